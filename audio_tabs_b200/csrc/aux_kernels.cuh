@@ -1,0 +1,123 @@
+// aux_kernels.cuh -- small non-template kernels (task table, stand-alone stages).  Included by
+// b200spec.cu only.
+#pragma once
+#include "frontend_kernel.cuh"
+
+namespace b2 {
+
+// ---- task table: tasks per clip = ceil(frames / chunk), exclusive prefix -> task_off -----------
+__global__ void k_setup_tasks(const long long *__restrict__ frame_off, int n_clips, int chunk,
+                              int *__restrict__ task_off, int *__restrict__ task_counter) {
+  __shared__ int s_part[1024];
+  const int t = threadIdx.x;
+  const int per = (n_clips + 1023) / 1024;
+  const int lo = min(t * per, n_clips), hi = min(lo + per, n_clips);
+  int sum = 0;
+  for (int c = lo; c < hi; ++c) sum += (int)((frame_off[c + 1] - frame_off[c] + chunk - 1) / chunk);
+  s_part[t] = sum;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {  // Hillis-Steele inclusive scan
+    int v = t >= d ? s_part[t - d] : 0;
+    __syncthreads();
+    s_part[t] += v;
+    __syncthreads();
+  }
+  int run = s_part[t] - sum;
+  for (int c = lo; c < hi; ++c) {
+    task_off[c] = run;
+    run += (int)((frame_off[c + 1] - frame_off[c] + chunk - 1) / chunk);
+  }
+  if (t == 1023) task_off[n_clips] = s_part[1023];
+  if (t == 0) *task_counter = 0;
+}
+
+// ---- stand-alone stages -------------------------------------------------------------------------
+__global__ void k_magnitude(const float2 *__restrict__ in, long long n, float *__restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float2 v = in[i];
+    out[i] = fast_sqrt(fmaf(v.x, v.x, v.y * v.y));
+  }
+}
+
+// one warp per row: y[j] = sum_i w[woff_j + i] * spec[row, start_j + i]; optional log10(mul*y+add)
+__global__ void k_filter_log(const float *__restrict__ spec, long long ld_spec, long long rows, int num_bins,
+                             int num_bands, const int *__restrict__ band_start, const int *__restrict__ band_len,
+                             const int *__restrict__ band_woff, const float *__restrict__ weights,
+                             int apply_filter, int apply_log, float mul, float add,
+                             float *__restrict__ out, long long ld_out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < rows; r += nwarps) {
+    const float *x = spec + r * ld_spec;
+    if (apply_filter) {
+      for (int j = 0; j < num_bands; ++j) {
+        const int st = band_start[j], len = band_len[j], wo = band_woff[j];
+        float acc = 0.f;
+        for (int i = lane; i < len; i += 32) acc = fmaf(weights[wo + i], x[st + i], acc);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+        if (lane == 0) {
+          if (apply_log) acc = log10f(__fadd_rn(__fmul_rn(mul, acc), add));
+          out[r * ld_out + j] = acc;
+        }
+      }
+    } else {
+      for (int j = lane; j < num_bins; j += 32) {
+        float y = x[j];
+        if (apply_log) y = log10f(__fadd_rn(__fmul_rn(mul, y), add));
+        out[r * ld_out + j] = y;
+      }
+    }
+  }
+}
+
+// one warp per row: lagged (positive) difference inside each clip, flux row sum, projection
+__global__ void k_diff_flux_proj(const float *__restrict__ L, long long ld_L, const long long *__restrict__ frame_off,
+                                 int n_clips, long long rows, int B, int kd, int positive, int num_classes,
+                                 const int *__restrict__ proj_off, const int *__restrict__ proj_band,
+                                 const float *__restrict__ proj_w, float *__restrict__ out, long long ld_out,
+                                 int col_spec, int col_diff, float *__restrict__ flux, float *__restrict__ proj,
+                                 long long ld_proj) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < rows; r += nwarps) {
+    int lo = 0, hi = n_clips;
+    while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (frame_off[mid] <= r) lo = mid; else hi = mid;
+    }
+    const long long local = r - frame_off[lo];
+    const float *x = L + r * ld_L;
+    float fsum = 0.f;
+    for (int j = lane; j < B; j += 32) {
+      const float v = x[j];
+      float D = 0.f;
+      if (kd > 0) {
+        if (local >= kd) D = v - L[(r - kd) * ld_L + j];
+        if (positive) D = fmaxf(D, 0.f);
+      }
+      if (out != nullptr) {
+        if (col_spec >= 0) out[r * ld_out + col_spec + j] = v;
+        if (col_diff >= 0) out[r * ld_out + col_diff + j] = D;
+      }
+      fsum += D;
+    }
+    if (flux != nullptr) {
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) fsum += __shfl_xor_sync(0xffffffffu, fsum, d);
+      if (lane == 0) flux[r] = fsum;
+    }
+    if (proj != nullptr) {
+      for (int c = lane; c < num_classes; c += 32) {
+        float acc = 0.f;
+        for (int i = proj_off[c]; i < proj_off[c + 1]; ++i) acc = fmaf(proj_w[i], x[proj_band[i]], acc);
+        proj[r * ld_proj + c] = acc;
+      }
+    }
+  }
+}
+
+}  // namespace b2

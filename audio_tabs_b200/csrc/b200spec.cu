@@ -1,0 +1,483 @@
+// b200spec.cu -- C ABI of libb200spec.so (see include/b200spec.h): plans, tables, launches.
+// No compute happens on the host; every entry point either fails loudly or launches sm_100a kernels.
+#include "../../include/b200spec.h"
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "aux_kernels.cuh"
+#include "front_inst.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CU_CHECK(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t e__ = (expr);                                                               \
+    if (e__ != cudaSuccess)                                                                 \
+      return fail(B200SPEC_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__));      \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  cudaError_t enter(int dev) {
+    cudaError_t e = cudaGetDevice(&prev);
+    if (e != cudaSuccess) return e;
+    if (prev != dev) {
+      e = cudaSetDevice(dev);
+      switched = (e == cudaSuccess);
+    }
+    return e;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
+struct ResPlan {
+  int frame_size = 0;
+  double hop = 0;
+  int origin = 0;
+  int num_bands = 0, nnz = 0, nseg = 0, kmax = 0;
+  int log_enabled = 0;
+  float mul = 1.f, add = 1.f;
+  int diff_frames = 0, positive = 0;
+  int num_classes = 0;
+  // device tables
+  float *d_window = nullptr;
+  float2 *d_tw2 = nullptr, *d_tw3 = nullptr, *d_pt = nullptr;
+  float *d_fbw = nullptr;
+  b2::Seg *d_segs = nullptr;
+  int *d_bseg = nullptr;
+  int *d_band_start = nullptr, *d_band_len = nullptr, *d_band_woff = nullptr;
+  int *d_proj_off = nullptr, *d_proj_band = nullptr;
+  float *d_proj_w = nullptr;
+};
+
+}  // namespace
+
+struct b200spec_plan {
+  int device = 0;
+  int dtype = 0;
+  int channels = 1;
+  int num_res = 0;
+  int num_sms = 0;
+  ResPlan res[B200SPEC_MAX_RES];
+  std::vector<void *> allocs;
+};
+
+namespace {
+
+template <class T>
+int upload(b200spec_plan *pl, const T *host, size_t n, T **out) {
+  *out = nullptr;
+  if (n == 0) n = 1;  // keep pointers valid
+  void *d = nullptr;
+  CU_CHECK(cudaMalloc(&d, n * sizeof(T)));
+  pl->allocs.push_back(d);
+  if (host) CU_CHECK(cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice));
+  else CU_CHECK(cudaMemset(d, 0, n * sizeof(T)));
+  *out = reinterpret_cast<T *>(d);
+  return 0;
+}
+
+int build_res(b200spec_plan *pl, const b200spec_res_desc &d, ResPlan &r) {
+  const int F = d.frame_size;
+  if (!(F == 1024 || F == 2048 || F == 4096 || F == 8192))
+    return fail(B200SPEC_ERR_UNSUPPORTED, "frame_size %d not supported (1024, 2048, 4096, 8192)", F);
+  if (!(d.hop_size > 0.0) || !std::isfinite(d.hop_size)) return fail(B200SPEC_ERR_ARG, "hop_size must be > 0");
+  if (d.window == nullptr) return fail(B200SPEC_ERR_ARG, "window is NULL");
+  if (d.num_bands < 0 || d.num_classes < 0 || d.num_classes > b2::kGroupThreads)
+    return fail(B200SPEC_ERR_ARG, "num_bands/num_classes out of range");
+  if (d.diff_frames < 0 || d.diff_frames > B200SPEC_MAX_DIFF_FRAMES)
+    return fail(B200SPEC_ERR_UNSUPPORTED, "diff_frames %d outside [0, %d]", d.diff_frames, B200SPEC_MAX_DIFF_FRAMES);
+  const int N = F / 2, R3 = N / 256;
+  const double PI = 3.14159265358979323846;
+  r.frame_size = F;
+  r.hop = d.hop_size;
+  r.origin = d.origin;
+  r.log_enabled = d.log_enabled;
+  r.mul = d.mul;
+  r.add = d.add;
+  r.diff_frames = d.diff_frames;
+  r.positive = d.positive_diffs;
+  r.num_bands = d.num_bands;
+  r.num_classes = d.num_classes;
+
+  // window: the real frame is packed as z[m] = x[2m] + i x[2m+1]; the 1/2 of the even/odd split
+  // E = (Z[k] + conj(Z[N-k])) / 2 is folded into the window (exact in binary floating point)
+  std::vector<float> win(F);
+  for (int i = 0; i < F; ++i) win[i] = 0.5f * d.window[i];
+  std::vector<float2> tw2(256), tw3(129 * R3), pt(129 * R3);
+  for (int k1 = 0; k1 < 16; ++k1)
+    for (int n2 = 0; n2 < 16; ++n2) {
+      double a = -2.0 * PI * (double)(n2 * k1) / 256.0;
+      tw2[k1 * 16 + n2] = make_float2((float)cos(a), (float)sin(a));
+    }
+  for (int q = 0; q <= 128; ++q)
+    for (int n3 = 0; n3 < R3; ++n3) {
+      double a = -2.0 * PI * (double)(n3 * q) / (double)N;
+      tw3[q * R3 + n3] = make_float2((float)cos(a), (float)sin(a));
+    }
+  for (int k3 = 0; k3 < R3; ++k3)
+    for (int q = 0; q <= 128; ++q) {
+      double a = -2.0 * PI * (double)(q + 256 * k3) / (double)F;
+      pt[k3 * 129 + q] = make_float2((float)sin(a), (float)-cos(a));  // -i * exp(i a)
+    }
+  int rc;
+  if ((rc = upload(pl, win.data(), win.size(), &r.d_window))) return rc;
+  if ((rc = upload(pl, tw2.data(), tw2.size(), &r.d_tw2))) return rc;
+  if ((rc = upload(pl, tw3.data(), tw3.size(), &r.d_tw3))) return rc;
+  if ((rc = upload(pl, pt.data(), pt.size(), &r.d_pt))) return rc;
+
+  // banded filterbank -> interleaved slices of at most `seg_max` taps
+  const int B = d.num_bands;
+  int nnz = 0, kmax = 0;
+  if (B > 0) {
+    if (!d.band_start || !d.band_len || !d.band_woff || !d.weights)
+      return fail(B200SPEC_ERR_ARG, "filterbank arrays are NULL");
+    for (int j = 0; j < B; ++j) {
+      if (d.band_len[j] < 0 || d.band_start[j] < 0 || d.band_start[j] + d.band_len[j] > N)
+        return fail(B200SPEC_ERR_ARG, "band %d covers bins outside [0, %d)", j, N);
+      if (d.band_woff[j] != nnz) return fail(B200SPEC_ERR_ARG, "band_woff must be the running sum of band_len");
+      nnz += d.band_len[j];
+      if (d.band_len[j] > 0 && d.band_start[j] + d.band_len[j] > kmax) kmax = d.band_start[j] + d.band_len[j];
+    }
+  }
+  r.nnz = nnz;
+  r.kmax = kmax;
+  int seg_max = (nnz + b2::kGroupThreads - 1) / b2::kGroupThreads;
+  if (seg_max < 8) seg_max = 8;
+  if (seg_max > 32) seg_max = 32;
+  std::vector<b2::Seg> segs;
+  std::vector<int> bseg(B + 1, 0);
+  for (int j = 0; j < B; ++j) {
+    bseg[j] = (int)segs.size();
+    const int L = d.band_len[j];
+    const int S = (L + seg_max - 1) / seg_max;
+    for (int i = 0; i < S; ++i) {
+      b2::Seg s;
+      s.k0 = d.band_start[j] + i;
+      s.w0 = d.band_woff[j] + i;
+      s.cnt = (L - i + S - 1) / S;
+      s.stride = S;
+      segs.push_back(s);
+    }
+  }
+  bseg[B] = (int)segs.size();
+  r.nseg = (int)segs.size();
+  if ((rc = upload(pl, d.weights, (size_t)nnz, &r.d_fbw))) return rc;
+  if ((rc = upload(pl, segs.data(), segs.size(), &r.d_segs))) return rc;
+  if ((rc = upload(pl, bseg.data(), bseg.size(), &r.d_bseg))) return rc;
+  if ((rc = upload(pl, d.band_start, (size_t)B, &r.d_band_start))) return rc;
+  if ((rc = upload(pl, d.band_len, (size_t)B, &r.d_band_len))) return rc;
+  if ((rc = upload(pl, d.band_woff, (size_t)B, &r.d_band_woff))) return rc;
+
+  if (d.num_classes > 0) {
+    if (!d.proj_off || !d.proj_band || !d.proj_weight) return fail(B200SPEC_ERR_ARG, "projection arrays are NULL");
+    const int np = d.proj_off[d.num_classes];
+    for (int i = 0; i < np; ++i)
+      if (d.proj_band[i] < 0 || d.proj_band[i] >= B) return fail(B200SPEC_ERR_ARG, "proj_band out of range");
+    if ((rc = upload(pl, d.proj_off, (size_t)d.num_classes + 1, &r.d_proj_off))) return rc;
+    if ((rc = upload(pl, d.proj_band, (size_t)np, &r.d_proj_band))) return rc;
+    if ((rc = upload(pl, d.proj_weight, (size_t)np, &r.d_proj_w))) return rc;
+  }
+  return 0;
+}
+
+struct Workspace {
+  int *counter;
+  int *task_off;
+};
+
+int carve_workspace(void *ws, size_t bytes, int n_clips, Workspace &w) {
+  if (ws == nullptr || bytes < b200spec_workspace_bytes(n_clips))
+    return fail(B200SPEC_ERR_ARG, "workspace too small: need %zu bytes", b200spec_workspace_bytes(n_clips));
+  w.counter = reinterpret_cast<int *>(ws);
+  w.task_off = reinterpret_cast<int *>(reinterpret_cast<char *>(ws) + 16);
+  return 0;
+}
+
+int choose_chunk(const b200spec_plan *pl, int F, long long total_frames, int kd) {
+  const int G = (F == 8192) ? 2 : 3;
+  const long long slots = (long long)pl->num_sms * G;
+  long long chunk = total_frames / (slots * 8);
+  const int lo = kd > 0 ? 16 : 4;
+  if (chunk < lo) chunk = lo;
+  if (chunk > 128) chunk = 128;
+  return (int)chunk;
+}
+
+int launch_front(const b200spec_plan *pl, int res, int mode, const void *d_sig, const int64_t *d_clip_off,
+                 const int64_t *d_frame_off, int n_clips, int64_t total_frames, b2::FrontParams &p,
+                 void *d_workspace, size_t workspace_bytes, void *stream) {
+  if (!pl) return fail(B200SPEC_ERR_ARG, "plan is NULL");
+  if (res < 0 || res >= pl->num_res) return fail(B200SPEC_ERR_ARG, "resolution %d out of range", res);
+  if (n_clips < 0 || total_frames < 0) return fail(B200SPEC_ERR_ARG, "negative sizes");
+  if (n_clips == 0 || total_frames == 0) return 0;
+  if (!d_sig || !d_clip_off || !d_frame_off) return fail(B200SPEC_ERR_ARG, "NULL device pointer");
+  const ResPlan &r = pl->res[res];
+  Workspace w;
+  int rc = carve_workspace(d_workspace, workspace_bytes, n_clips, w);
+  if (rc) return rc;
+  DeviceGuard guard;
+  CU_CHECK(guard.enter(pl->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+  const int chunk = choose_chunk(pl, r.frame_size, total_frames, mode == b2::MODE_LOGFILT ? r.diff_frames : 0);
+  b2::k_setup_tasks<<<1, 1024, 0, st>>>(reinterpret_cast<const long long *>(d_frame_off), n_clips, chunk,
+                                         w.task_off, w.counter);
+  CU_CHECK(cudaGetLastError());
+  g_launches++;
+
+  p.sig = d_sig;
+  p.clip_off = reinterpret_cast<const long long *>(d_clip_off);
+  p.frame_off = reinterpret_cast<const long long *>(d_frame_off);
+  p.n_clips = n_clips;
+  p.task_off = w.task_off;
+  p.task_counter = w.counter;
+  p.chunk = chunk;
+  p.hop = r.hop;
+  p.origin = r.origin;
+  p.window = r.d_window;
+  p.tw2 = r.d_tw2;
+  p.tw3 = r.d_tw3;
+  p.pt = r.d_pt;
+  p.num_bands = r.num_bands;
+  p.nnz = r.nnz;
+  p.nseg = r.nseg;
+  p.kmax = r.kmax;
+  p.fbw = r.d_fbw;
+  p.segs = r.d_segs;
+  p.bseg = r.d_bseg;
+  p.log_enabled = r.log_enabled;
+  p.mul = r.mul;
+  p.add = r.add;
+  p.diff_frames = r.diff_frames;
+  p.positive = r.positive;
+  p.proj_off = r.d_proj_off;
+  p.proj_band = r.d_proj_band;
+  p.proj_w = r.d_proj_w;
+
+  const int in = (pl->dtype == B200SPEC_I16 ? 2 : 0) + (pl->channels == 2 ? 1 : 0);
+  const long long task_bound = total_frames / chunk + n_clips;
+  cudaError_t e;
+  switch (r.frame_size) {
+    case 1024: e = b2_launch_front_1024(in, mode, p, pl->num_sms, task_bound, st); break;
+    case 2048: e = b2_launch_front_2048(in, mode, p, pl->num_sms, task_bound, st); break;
+    case 4096: e = b2_launch_front_4096(in, mode, p, pl->num_sms, task_bound, st); break;
+    default: e = b2_launch_front_8192(in, mode, p, pl->num_sms, task_bound, st); break;
+  }
+  if (e != cudaSuccess) return fail(B200SPEC_ERR_CUDA, "front-end kernel launch failed: %s", cudaGetErrorString(e));
+  g_launches++;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200spec_abi_version(void) { return B200SPEC_ABI_VERSION; }
+
+const char *b200spec_last_error(void) { return g_last_error.c_str(); }
+
+int b200spec_num_frames(int64_t n_samples, double hop_size, int end_mode, int64_t *out) {
+  if (!out) return fail(B200SPEC_ERR_ARG, "out is NULL");
+  if (n_samples < 0 || !(hop_size > 0.0)) return fail(B200SPEC_ERR_ARG, "n_samples < 0 or hop_size <= 0");
+  const double q = (double)n_samples / hop_size;  // same float64 division numpy performs
+  if (end_mode == B200SPEC_END_NORMAL) *out = (int64_t)std::ceil(q);
+  else if (end_mode == B200SPEC_END_EXTEND) *out = (int64_t)std::floor(q + 1.0);
+  else return fail(B200SPEC_ERR_ARG, "end of signal handling '%d' unknown", end_mode);
+  return 0;
+}
+
+int b200spec_frame_start(int64_t index, double hop_size, int32_t frame_size, int32_t origin, int64_t *out) {
+  if (!out) return fail(B200SPEC_ERR_ARG, "out is NULL");
+  *out = (int64_t)((double)index * hop_size) - frame_size / 2 - origin;  // int() truncates like Python
+  return 0;
+}
+
+int b200spec_plan_create(const b200spec_plan_desc *desc, b200spec_plan **out) {
+  if (!desc || !out) return fail(B200SPEC_ERR_ARG, "desc/out is NULL");
+  *out = nullptr;
+  if (desc->num_res < 1 || desc->num_res > B200SPEC_MAX_RES)
+    return fail(B200SPEC_ERR_ARG, "num_res %d outside [1, %d]", desc->num_res, B200SPEC_MAX_RES);
+  if (desc->dtype != B200SPEC_F32 && desc->dtype != B200SPEC_I16) return fail(B200SPEC_ERR_ARG, "unknown dtype");
+  if (desc->channels != 1 && desc->channels != 2)
+    return fail(B200SPEC_ERR_UNSUPPORTED, "channels must be 1 or 2 (got %d)", desc->channels);
+  int ndev = 0;
+  CU_CHECK(cudaGetDeviceCount(&ndev));
+  if (desc->device < 0 || desc->device >= ndev)
+    return fail(B200SPEC_ERR_ARG, "device %d not present (%d devices)", desc->device, ndev);
+  cudaDeviceProp prop;
+  CU_CHECK(cudaGetDeviceProperties(&prop, desc->device));
+  if (prop.major != 10)
+    return fail(B200SPEC_ERR_ARCH, "device %d is sm_%d%d; this library only carries sm_100a code", desc->device,
+                prop.major, prop.minor);
+  DeviceGuard guard;
+  CU_CHECK(guard.enter(desc->device));
+  b200spec_plan *pl = new b200spec_plan();
+  pl->device = desc->device;
+  pl->dtype = desc->dtype;
+  pl->channels = desc->channels;
+  pl->num_res = desc->num_res;
+  pl->num_sms = prop.multiProcessorCount;
+  for (int i = 0; i < desc->num_res; ++i) {
+    int rc = build_res(pl, desc->res[i], pl->res[i]);
+    if (rc) {
+      b200spec_plan_destroy(pl);
+      return rc;
+    }
+  }
+  *out = pl;
+  return 0;
+}
+
+int b200spec_plan_destroy(b200spec_plan *plan) {
+  if (!plan) return 0;
+  DeviceGuard guard;
+  guard.enter(plan->device);
+  for (void *d : plan->allocs) cudaFree(d);
+  delete plan;
+  return 0;
+}
+
+size_t b200spec_workspace_bytes(int32_t n_clips) {
+  if (n_clips < 0) n_clips = 0;
+  return 16 + sizeof(int) * ((size_t)n_clips + 1) + 16;
+}
+
+int b200spec_stft(const b200spec_plan *plan, int32_t res, const void *d_sig, const int64_t *d_clip_off,
+                  const int64_t *d_frame_off, int32_t n_clips, int64_t total_frames, float *d_out,
+                  void *d_workspace, size_t workspace_bytes, void *stream) {
+  if (!d_out && total_frames > 0) return fail(B200SPEC_ERR_ARG, "d_out is NULL");
+  b2::FrontParams p{};
+  p.spec_out = d_out;
+  p.spec_complex = 1;
+  return launch_front(plan, res, b2::MODE_SPECTRUM, d_sig, d_clip_off, d_frame_off, n_clips, total_frames, p,
+                      d_workspace, workspace_bytes, stream);
+}
+
+int b200spec_spectrogram(const b200spec_plan *plan, int32_t res, const void *d_sig, const int64_t *d_clip_off,
+                         const int64_t *d_frame_off, int32_t n_clips, int64_t total_frames, float *d_out,
+                         void *d_workspace, size_t workspace_bytes, void *stream) {
+  if (!d_out && total_frames > 0) return fail(B200SPEC_ERR_ARG, "d_out is NULL");
+  b2::FrontParams p{};
+  p.spec_out = d_out;
+  p.spec_complex = 0;
+  return launch_front(plan, res, b2::MODE_SPECTRUM, d_sig, d_clip_off, d_frame_off, n_clips, total_frames, p,
+                      d_workspace, workspace_bytes, stream);
+}
+
+int b200spec_logfilt(const b200spec_plan *plan, int32_t res, const void *d_sig, const int64_t *d_clip_off,
+                     const int64_t *d_frame_off, int32_t n_clips, int64_t total_frames,
+                     const b200spec_out_desc *out, void *d_workspace, size_t workspace_bytes, void *stream) {
+  if (!plan) return fail(B200SPEC_ERR_ARG, "plan is NULL");
+  if (!out) return fail(B200SPEC_ERR_ARG, "out descriptor is NULL");
+  if (res < 0 || res >= plan->num_res) return fail(B200SPEC_ERR_ARG, "resolution %d out of range", res);
+  const ResPlan &r = plan->res[res];
+  if (r.num_bands <= 0) return fail(B200SPEC_ERR_ARG, "resolution %d has no filterbank; use b200spec_spectrogram", res);
+  if (out->d_proj && r.num_classes <= 0) return fail(B200SPEC_ERR_ARG, "d_proj given but the plan has no projection");
+  if (out->d_out && out->ld_out < r.num_bands) return fail(B200SPEC_ERR_ARG, "ld_out smaller than num_bands");
+  if (out->col_diff >= 0 && r.diff_frames <= 0) return fail(B200SPEC_ERR_ARG, "col_diff given but diff_frames == 0");
+  b2::FrontParams p{};
+  p.out = out->d_out;
+  p.ld_out = out->ld_out;
+  p.col_spec = out->col_spec;
+  p.col_diff = out->col_diff;
+  p.flux = out->d_flux;
+  p.proj = out->d_proj;
+  p.ld_proj = out->ld_proj;
+  p.num_classes = out->d_proj ? r.num_classes : 0;
+  return launch_front(plan, res, b2::MODE_LOGFILT, d_sig, d_clip_off, d_frame_off, n_clips, total_frames, p,
+                      d_workspace, workspace_bytes, stream);
+}
+
+int b200spec_magnitude(const float *d_stft, int64_t n_elems, float *d_out, void *stream) {
+  if (n_elems < 0) return fail(B200SPEC_ERR_ARG, "n_elems < 0");
+  if (n_elems == 0) return 0;
+  if (!d_stft || !d_out) return fail(B200SPEC_ERR_ARG, "NULL device pointer");
+  long long blocks = (n_elems + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  b2::k_magnitude<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float2 *>(d_stft), n_elems, d_out);
+  CU_CHECK(cudaGetLastError());
+  g_launches++;
+  return 0;
+}
+
+int b200spec_filter_log(const b200spec_plan *plan, int32_t res, const float *d_spec, int64_t ld_spec,
+                        int64_t total_frames, int32_t apply_filter, int32_t apply_log, float *d_out,
+                        int64_t ld_out, void *stream) {
+  if (!plan) return fail(B200SPEC_ERR_ARG, "plan is NULL");
+  if (res < 0 || res >= plan->num_res) return fail(B200SPEC_ERR_ARG, "resolution %d out of range", res);
+  if (total_frames < 0) return fail(B200SPEC_ERR_ARG, "total_frames < 0");
+  if (total_frames == 0) return 0;
+  if (!d_spec || !d_out) return fail(B200SPEC_ERR_ARG, "NULL device pointer");
+  const ResPlan &r = plan->res[res];
+  if (apply_filter && r.num_bands <= 0) return fail(B200SPEC_ERR_ARG, "resolution has no filterbank");
+  DeviceGuard guard;
+  CU_CHECK(guard.enter(plan->device));
+  long long blocks = (total_frames + 7) / 8;
+  if (blocks > plan->num_sms * 8) blocks = plan->num_sms * 8;
+  const int num_bins = apply_filter ? r.frame_size / 2 : (int)ld_spec;
+  b2::k_filter_log<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      d_spec, ld_spec, total_frames, num_bins, r.num_bands, r.d_band_start, r.d_band_len, r.d_band_woff, r.d_fbw,
+      apply_filter, apply_log, r.mul, r.add, d_out, ld_out);
+  CU_CHECK(cudaGetLastError());
+  g_launches++;
+  return 0;
+}
+
+int b200spec_diff_flux_chroma(const b200spec_plan *plan, int32_t res, const float *d_L, int64_t ld_L,
+                              const int64_t *d_frame_off, int32_t n_clips, int64_t total_frames,
+                              const b200spec_out_desc *out, void *stream) {
+  if (!plan || !out) return fail(B200SPEC_ERR_ARG, "plan/out is NULL");
+  if (res < 0 || res >= plan->num_res) return fail(B200SPEC_ERR_ARG, "resolution %d out of range", res);
+  if (total_frames < 0 || n_clips < 0) return fail(B200SPEC_ERR_ARG, "negative sizes");
+  if (total_frames == 0 || n_clips == 0) return 0;
+  if (!d_L || !d_frame_off) return fail(B200SPEC_ERR_ARG, "NULL device pointer");
+  const ResPlan &r = plan->res[res];
+  if (out->d_proj && r.num_classes <= 0) return fail(B200SPEC_ERR_ARG, "d_proj given but the plan has no projection");
+  const int B = r.num_bands > 0 ? r.num_bands : (int)ld_L;
+  DeviceGuard guard;
+  CU_CHECK(guard.enter(plan->device));
+  long long blocks = (total_frames + 7) / 8;
+  if (blocks > plan->num_sms * 8) blocks = plan->num_sms * 8;
+  b2::k_diff_flux_proj<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      d_L, ld_L, reinterpret_cast<const long long *>(d_frame_off), n_clips, total_frames, B, r.diff_frames,
+      r.positive, out->d_proj ? r.num_classes : 0, r.d_proj_off, r.d_proj_band, r.d_proj_w, out->d_out,
+      out->ld_out, out->col_spec, out->col_diff, out->d_flux, out->d_proj, out->ld_proj);
+  CU_CHECK(cudaGetLastError());
+  g_launches++;
+  return 0;
+}
+
+int b200spec_plan_num_res(const b200spec_plan *plan) { return plan ? plan->num_res : 0; }
+
+int b200spec_plan_num_bands(const b200spec_plan *plan, int32_t res) {
+  if (!plan || res < 0 || res >= plan->num_res) return -1;
+  return plan->res[res].num_bands;
+}
+
+int64_t b200spec_launch_count(void) { return g_launches.load(); }
+
+}  // extern "C"

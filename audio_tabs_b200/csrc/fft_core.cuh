@@ -1,0 +1,235 @@
+// fft_core.cuh -- register-level butterflies and the three thread-mapped passes of the
+// frame FFT used by every front-end kernel.
+//
+// Replaces the inner loop of madmom.audio.stft.stft() (per-frame scipy.fftpack.fft, reached from
+// /root/reference/backend/app/services/grid/beats.py:74 via RNNBeatProcessor).
+//
+// A real frame of F samples is transformed as ONE complex FFT of N = F/2 points on
+// z[m] = x[2m] + i x[2m+1] (window folded into the load, pre-scaled by 1/2), followed by the
+// even/odd split  X[k] = E[k] + W_F^k O[k].  N = 16 * 16 * R3 with R3 = F/512 in {2,4,8,16}:
+//
+//   pass 1  thread b in [0,16*R3):  DFT16 over n1 of z[n1*16*R3 + b]            -> buf1[k1][b]
+//   pass 2  thread (k1,n3):         twiddle W_256^(n2*k1), DFT16 over n2       -> buf2[n3][k1+16*k2]
+//   pass 3  unit u in [0,128):      butterflies q=u and q=256-u of radix R3 are combined BEFORE the
+//           DFT (P = a + conj(b), M = a - conj(b)), so E and O come out of two DFT_R3 directly and
+//           both bins k and N-k of the real spectrum are produced in registers.
+//
+// Everything here is __host__ __device__ so tests/emu can run the exact thread mapping on the CPU
+// (test infrastructure only; the product path is the CUDA build).
+#pragma once
+
+#if defined(__CUDACC__)
+#define B2_HD __host__ __device__ __forceinline__
+#else
+#include <cmath>
+#define B2_HD inline
+struct float2 {
+  float x, y;
+};
+static inline float2 make_float2(float x, float y) {
+  float2 r;
+  r.x = x;
+  r.y = y;
+  return r;
+}
+#endif
+
+namespace b2 {
+
+constexpr int kGroupThreads = 128;  // threads cooperating on one frame (or FPG small frames)
+
+template <int F>
+struct FftCfg {
+  static_assert(F == 1024 || F == 2048 || F == 4096 || F == 8192, "unsupported frame size");
+  static constexpr int N = F / 2;          // complex FFT length
+  static constexpr int R3 = N / 256;       // radix of the last pass
+  static constexpr int BPF = 16 * R3;      // radix-16 butterflies per frame in pass 1 and pass 2
+  static constexpr int FPG = (BPF >= kGroupThreads) ? 1 : kGroupThreads / BPF;  // frames per group step
+  static constexpr int IT12 = (BPF >= kGroupThreads) ? BPF / kGroupThreads : 1; // pass-1/2 butterflies per thread
+  static constexpr int S1 = BPF + 1;       // buf1 row stride (float2), +1 keeps pass-2 reads conflict free
+  static constexpr int BUF1 = 16 * S1;     // float2 elements per frame
+  static constexpr int BUF2 = N;           // float2 elements per frame
+  static constexpr int TW3 = 129 * R3;     // tw3[q*R3 + n3] = W_N^(n3*q), q in [0,128]
+  static constexpr int PT = 129 * R3;      // pt[k3*129 + q] = -i * W_F^(q + 256*k3)
+};
+
+// ---- complex helpers ---------------------------------------------------------------------------
+B2_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+B2_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+B2_HD float2 cmul(float2 a, float2 b) {
+  return make_float2(fmaf(a.x, b.x, -(a.y * b.y)), fmaf(a.x, b.y, a.y * b.x));
+}
+B2_HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+B2_HD float2 mul_neg_i(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
+
+constexpr float kH = 0.70710678118654752440f;   // sqrt(1/2)
+constexpr float kC1 = 0.92387953251128675613f;  // cos(pi/8)
+constexpr float kS1 = 0.38268343236508977173f;  // sin(pi/8)
+
+B2_HD float2 mul_w8_1(float2 a) { return make_float2(kH * (a.x + a.y), kH * (a.y - a.x)); }    // * (h,-h)
+B2_HD float2 mul_w8_3(float2 a) { return make_float2(kH * (a.y - a.x), -kH * (a.x + a.y)); }   // * (-h,-h)
+
+// ---- in-register DFTs (forward, W = exp(-2 pi i / R)) ------------------------------------------
+B2_HD void dft2(float2 &a, float2 &b) {
+  float2 t = csub(a, b);
+  a = cadd(a, b);
+  b = t;
+}
+
+// natural order in, natural order out
+B2_HD void dft4(float2 &x0, float2 &x1, float2 &x2, float2 &x3) {
+  float2 t0 = cadd(x0, x2), t1 = csub(x0, x2);
+  float2 t2 = cadd(x1, x3), t3 = mul_neg_i(csub(x1, x3));
+  x0 = cadd(t0, t2);
+  x2 = csub(t0, t2);
+  x1 = cadd(t1, t3);
+  x3 = csub(t1, t3);
+}
+
+// in place; X[k] ends up at v[pos8(k)]
+B2_HD void dft8(float2 (&v)[8]) {
+  dft4(v[0], v[2], v[4], v[6]);  // n2 = 0: y[0][k1] at v[2*k1]
+  dft4(v[1], v[3], v[5], v[7]);  // n2 = 1: y[1][k1] at v[2*k1+1]
+  v[3] = mul_w8_1(v[3]);
+  v[5] = mul_neg_i(v[5]);
+  v[7] = mul_w8_3(v[7]);
+  dft2(v[0], v[1]);
+  dft2(v[2], v[3]);
+  dft2(v[4], v[5]);
+  dft2(v[6], v[7]);
+}
+
+// in place; X[k] ends up at v[pos16(k)]
+B2_HD void dft16(float2 (&v)[16]) {
+#pragma unroll
+  for (int n2 = 0; n2 < 4; ++n2) dft4(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);  // y[n2][k1] at v[4*k1+n2]
+  // twiddle y[n2][k1] *= W16^(n2*k1)
+  v[5] = cmul(v[5], make_float2(kC1, -kS1));    // (1,1) W^1
+  v[9] = mul_w8_1(v[9]);                        // (n2=1,k1=2) W^2
+  v[13] = cmul(v[13], make_float2(kS1, -kC1));  // (1,3) W^3
+  v[6] = mul_w8_1(v[6]);                        // (2,1) W^2
+  v[10] = mul_neg_i(v[10]);                     // (2,2) W^4
+  v[14] = mul_w8_3(v[14]);                      // (2,3) W^6
+  v[7] = cmul(v[7], make_float2(kS1, -kC1));    // (3,1) W^3
+  v[11] = mul_w8_3(v[11]);                      // (3,2) W^6
+  v[15] = cmul(v[15], make_float2(-kC1, kS1));  // (3,3) W^9
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1) dft4(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
+}
+
+// index in v[] that holds output bin k after the in-place DFT of radix R
+template <int R>
+B2_HD constexpr int dft_pos(int k) {
+  return R == 16 ? (((k & 3) << 2) | (k >> 2)) : R == 8 ? (2 * (k & 3) + (k >> 2)) : k;
+}
+
+template <int R>
+struct Dft;
+template <>
+struct Dft<2> {
+  static B2_HD void run(float2 (&v)[2]) { dft2(v[0], v[1]); }
+};
+template <>
+struct Dft<4> {
+  static B2_HD void run(float2 (&v)[4]) { dft4(v[0], v[1], v[2], v[3]); }
+};
+template <>
+struct Dft<8> {
+  static B2_HD void run(float2 (&v)[8]) { dft8(v); }
+};
+template <>
+struct Dft<16> {
+  static B2_HD void run(float2 (&v)[16]) { dft16(v); }
+};
+
+// ---- pass 1: windowed load + DFT16 over n1 -----------------------------------------------------
+// `load(m)` returns the windowed complex sample z[m], m in [0, N).
+template <int F, class Load>
+B2_HD void fft_pass1(int b, Load load, float2 *buf1) {
+  using C = FftCfg<F>;
+  float2 v[16];
+#pragma unroll
+  for (int n1 = 0; n1 < 16; ++n1) v[n1] = load(n1 * C::BPF + b);
+  dft16(v);
+#pragma unroll
+  for (int k1 = 0; k1 < 16; ++k1) buf1[k1 * C::S1 + b] = v[dft_pos<16>(k1)];
+}
+
+// ---- pass 2: twiddle W_256^(n2*k1), DFT16 over n2 ----------------------------------------------
+// t2 in [0, BPF): k1 = t2 % 16, n3 = t2 / 16.  tw2[n2] = W_256^(n2*k1) for this thread's k1.
+template <int F>
+B2_HD void fft_pass2(int t2, const float2 (&tw2)[16], const float2 *buf1, float2 *buf2) {
+  using C = FftCfg<F>;
+  const int k1 = t2 & 15, n3 = t2 >> 4;
+  float2 v[16];
+#pragma unroll
+  for (int n2 = 0; n2 < 16; ++n2) v[n2] = buf1[k1 * C::S1 + n2 * C::R3 + n3];
+#pragma unroll
+  for (int n2 = 1; n2 < 16; ++n2) v[n2] = cmul(v[n2], tw2[n2]);
+  dft16(v);
+#pragma unroll
+  for (int k2 = 0; k2 < 16; ++k2) buf2[n3 * 256 + k1 + 16 * k2] = v[dft_pos<16>(k2)];
+}
+
+// ---- pass 3: last radix-R3 pass fused with the real-spectrum split -----------------------------
+// unit u in [1,127]: emits bins k = u + 256*k3 and N - k.   emit(k, X) receives each bin once.
+template <int F, class Emit>
+B2_HD void fft_pass3_unit(int u, const float2 *buf2, const float2 *tw3, const float2 *pt, Emit emit) {
+  using C = FftCfg<F>;
+  constexpr int R3 = C::R3;
+  float2 P[R3], M[R3];
+#pragma unroll
+  for (int n3 = 0; n3 < R3; ++n3) {
+    float2 a = buf2[n3 * 256 + u];
+    float2 b = buf2[n3 * 256 + 256 - u];
+    P[n3] = make_float2(a.x + b.x, a.y - b.y);  // a + conj(b)
+    M[n3] = make_float2(a.x - b.x, a.y + b.y);  // a - conj(b)
+  }
+#pragma unroll
+  for (int n3 = 1; n3 < R3; ++n3) {
+    float2 w = tw3[u * R3 + n3];
+    P[n3] = cmul(P[n3], w);
+    M[n3] = cmul(M[n3], w);
+  }
+  Dft<R3>::run(P);
+  Dft<R3>::run(M);
+#pragma unroll
+  for (int k3 = 0; k3 < R3; ++k3) {
+    float2 E = P[dft_pos<R3>(k3)];
+    float2 T = cmul(M[dft_pos<R3>(k3)], pt[k3 * 129 + u]);
+    const int k = u + 256 * k3;
+    emit(k, cadd(E, T));
+    emit(C::N - k, cconj(csub(E, T)));
+  }
+}
+
+// unit 0: the two self-paired butterflies q = 0 (bins 256*k3) and q = 128 (bins 128 + 256*k3)
+template <int F, class Emit>
+B2_HD void fft_pass3_unit0(const float2 *buf2, const float2 *tw3, const float2 *pt, Emit emit) {
+  using C = FftCfg<F>;
+  constexpr int R3 = C::R3;
+  float2 Z[R3];
+#pragma unroll
+  for (int n3 = 0; n3 < R3; ++n3) Z[n3] = buf2[n3 * 256];
+  Dft<R3>::run(Z);
+#pragma unroll
+  for (int k3 = 0; k3 < R3; ++k3) {
+    float2 a = Z[dft_pos<R3>(k3)];
+    float2 b = cconj(Z[dft_pos<R3>((R3 - k3) % R3)]);
+    emit(256 * k3, cadd(cadd(a, b), cmul(csub(a, b), pt[k3 * 129])));
+  }
+#pragma unroll
+  for (int n3 = 0; n3 < R3; ++n3) {
+    float2 a = buf2[n3 * 256 + 128];
+    Z[n3] = n3 == 0 ? a : cmul(a, tw3[128 * R3 + n3]);
+  }
+  Dft<R3>::run(Z);
+#pragma unroll
+  for (int k3 = 0; k3 < R3; ++k3) {
+    float2 a = Z[dft_pos<R3>(k3)];
+    float2 b = cconj(Z[dft_pos<R3>(R3 - 1 - k3)]);
+    emit(128 + 256 * k3, cadd(cadd(a, b), cmul(csub(a, b), pt[k3 * 129 + 128])));
+  }
+}
+
+}  // namespace b2

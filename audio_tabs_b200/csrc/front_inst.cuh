@@ -1,0 +1,55 @@
+// front_inst.cuh -- instantiates k_front for one frame size (one translation unit per size so the
+// sizes compile in parallel) and exposes a plain launcher to b200spec.cu.
+#pragma once
+#include "frontend_kernel.cuh"
+
+namespace b2 {
+
+// groups of 128 threads per CTA for each frame size (bounded by shared memory and registers)
+template <int F>
+struct GroupsPerCta {
+  static constexpr int value = (F == 8192) ? 2 : 3;
+};
+
+struct LaunchResult {
+  cudaError_t err;
+  int launches;
+};
+
+template <int F, int IN, int MODE>
+static cudaError_t launch_one(FrontParams &p, int num_sms, long long task_bound, cudaStream_t st) {
+  constexpr int G = GroupsPerCta<F>::value;
+  const size_t smem = front_smem_layout<F>(p, MODE, G);
+  auto kern = k_front<F, IN, MODE, G>;
+  // per device and cheap; set on every launch so multi-device processes stay correct
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  long long ctas = (task_bound + G - 1) / G;
+  int grid = (int)(ctas < num_sms ? (ctas < 1 ? 1 : ctas) : num_sms);
+  kern<<<grid, kGroupThreads * G, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+template <int F>
+static cudaError_t launch_front_size(int in, int mode, FrontParams &p, int num_sms, long long task_bound,
+                                     cudaStream_t st) {
+  switch (in * 2 + mode) {
+    case IN_F32_MONO * 2 + MODE_LOGFILT: return launch_one<F, IN_F32_MONO, MODE_LOGFILT>(p, num_sms, task_bound, st);
+    case IN_F32_MONO * 2 + MODE_SPECTRUM: return launch_one<F, IN_F32_MONO, MODE_SPECTRUM>(p, num_sms, task_bound, st);
+    case IN_F32_STEREO * 2 + MODE_LOGFILT: return launch_one<F, IN_F32_STEREO, MODE_LOGFILT>(p, num_sms, task_bound, st);
+    case IN_F32_STEREO * 2 + MODE_SPECTRUM: return launch_one<F, IN_F32_STEREO, MODE_SPECTRUM>(p, num_sms, task_bound, st);
+    case IN_I16_MONO * 2 + MODE_LOGFILT: return launch_one<F, IN_I16_MONO, MODE_LOGFILT>(p, num_sms, task_bound, st);
+    case IN_I16_MONO * 2 + MODE_SPECTRUM: return launch_one<F, IN_I16_MONO, MODE_SPECTRUM>(p, num_sms, task_bound, st);
+    case IN_I16_STEREO * 2 + MODE_LOGFILT: return launch_one<F, IN_I16_STEREO, MODE_LOGFILT>(p, num_sms, task_bound, st);
+    case IN_I16_STEREO * 2 + MODE_SPECTRUM: return launch_one<F, IN_I16_STEREO, MODE_SPECTRUM>(p, num_sms, task_bound, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace b2
+
+// declared here, defined in front_f<F>.cu
+cudaError_t b2_launch_front_1024(int in, int mode, b2::FrontParams &p, int num_sms, long long task_bound, cudaStream_t st);
+cudaError_t b2_launch_front_2048(int in, int mode, b2::FrontParams &p, int num_sms, long long task_bound, cudaStream_t st);
+cudaError_t b2_launch_front_4096(int in, int mode, b2::FrontParams &p, int num_sms, long long task_bound, cudaStream_t st);
+cudaError_t b2_launch_front_8192(int in, int mode, b2::FrontParams &p, int num_sms, long long task_bound, cudaStream_t st);

@@ -1,0 +1,368 @@
+// frontend_kernel.cuh -- the fused front-end kernel (K1 framing+window+FFT, K2 magnitude+filterbank
+// +log, K3 difference/flux/projection) as one persistent sm_100a kernel per resolution.
+//
+// Replaces, for one resolution, the madmom 0.16.1 chain that
+// /root/reference/backend/app/services/grid/beats.py:74 (RNNBeatProcessor),
+// chords/extract.py:54 (DeepChromaProcessor) and theory/key.py:101 (CNNKeyRecognitionProcessor) run:
+//   signal_frame -> frame*fft_window -> fftpack.fft[:F/2] -> np.abs -> np.dot(., filterbank)
+//   -> np.log10(mul*y+add) -> SpectrogramDifference(positive) -> np.hstack
+//
+// Execution model
+//   grid   = one CTA per SM (persistent), G groups of 128 threads per CTA
+//   group  = pulls tasks (clip, chunk of frames) from a global counter; processes FPG frames per
+//            step entirely in shared memory; named barriers (bar.sync id,128) keep groups independent
+//   tables = window / twiddles / banded filterbank are staged once per CTA in shared memory,
+//            pass-2 twiddles live in registers
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fft_core.cuh"
+
+namespace b2 {
+
+enum InputKind { IN_F32_MONO = 0, IN_F32_STEREO = 1, IN_I16_MONO = 2, IN_I16_STEREO = 3 };
+enum KernelMode { MODE_LOGFILT = 0, MODE_SPECTRUM = 1 };
+
+struct Seg {      // one interleaved slice of a filterbank band
+  int k0;         // first FFT bin
+  int w0;         // first weight index
+  int cnt;        // number of taps
+  int stride;     // tap stride in bins (= number of slices of the band)
+};
+
+struct FrontParams {
+  // input
+  const void *sig;
+  const long long *clip_off;
+  const long long *frame_off;
+  int n_clips;
+  const int *task_off;  // n_clips + 1 (workspace, written by k_setup_tasks)
+  int *task_counter;    // workspace
+  int chunk;            // frames per task
+  double hop;
+  int origin;
+  // tables (plan-owned, device)
+  const float *window;  // F, already * 1/2 (and / 32767 for int16)
+  const float2 *tw2;    // [16][16]
+  const float2 *tw3;    // [129][R3]
+  const float2 *pt;     // [R3][129]
+  // filterbank (MODE_LOGFILT)
+  int num_bands, nnz, nseg, kmax;
+  const float *fbw;
+  const Seg *segs;
+  const int *bseg;      // num_bands + 1
+  int log_enabled;
+  float mul, add;
+  int diff_frames, positive;
+  int num_classes;
+  const int *proj_off, *proj_band;
+  const float *proj_w;
+  // outputs (MODE_LOGFILT)
+  float *out;
+  long long ld_out;
+  int col_spec, col_diff;
+  float *flux;
+  float *proj;
+  long long ld_proj;
+  // outputs (MODE_SPECTRUM)
+  float *spec_out;      // (rows, N) float or float2
+  int spec_complex;
+  // shared-memory carve-up (byte offsets), filled by front_smem_layout()
+  int o_win, o_tw3, o_pt, o_fbw, o_segs, o_bseg, o_groups, group_bytes;
+  int g_buf2, g_partial, g_hist, g_lrow, g_red, g_task;  // offsets inside a group's block
+};
+
+template <int F>
+inline size_t front_smem_layout(FrontParams &p, int mode, int G) {
+  using C = FftCfg<F>;
+  auto al = [](size_t v) { return (v + 15) & ~size_t(15); };
+  size_t o = 0;
+  p.o_win = (int)o; o = al(o + sizeof(float) * F);
+  p.o_tw3 = (int)o; o = al(o + sizeof(float2) * C::TW3);
+  p.o_pt = (int)o;  o = al(o + sizeof(float2) * C::PT);
+  p.o_fbw = p.o_segs = p.o_bseg = (int)o;
+  if (mode == MODE_LOGFILT) {
+    p.o_fbw = (int)o;  o = al(o + sizeof(float) * p.nnz);
+    p.o_segs = (int)o; o = al(o + sizeof(Seg) * p.nseg);
+    p.o_bseg = (int)o; o = al(o + sizeof(int) * (p.num_bands + 1));
+  }
+  p.o_groups = (int)o;
+  size_t g = 0;
+  g = al(g + sizeof(float2) * C::FPG * C::BUF1);  // buf1 (magnitudes alias it after pass 2)
+  p.g_buf2 = (int)g;    g = al(g + sizeof(float2) * C::FPG * C::BUF2);
+  p.g_partial = p.g_hist = p.g_lrow = (int)g;
+  if (mode == MODE_LOGFILT) {
+    p.g_partial = (int)g; g = al(g + sizeof(float) * C::FPG * p.nseg);
+    p.g_hist = (int)g;    g = al(g + sizeof(float) * (p.diff_frames > 0 ? p.diff_frames : 1) * p.num_bands);
+    p.g_lrow = (int)g;    g = al(g + sizeof(float) * C::FPG * p.num_bands);
+  }
+  p.g_red = (int)g;  g = al(g + sizeof(float) * 4 * C::FPG);
+  p.g_task = (int)g; g = al(g + 16);
+  p.group_bytes = (int)g;
+  return o + g * G;
+}
+
+#if defined(__CUDACC__)
+
+__device__ __forceinline__ void group_bar(int g) {
+  asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(kGroupThreads) : "memory");
+}
+
+__device__ __forceinline__ float fast_sqrt(float v) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v));  // max rel. error 2^-23
+  return r;
+}
+
+// ---- sample access: madmom Signal dtype + remix (audio/signal.py) ------------------------------
+template <int IN>
+struct Samples {
+  const void *base;  // first sample of the clip
+  __device__ __forceinline__ float at(long long s) const {
+    if (IN == IN_F32_MONO) {
+      return __ldg(reinterpret_cast<const float *>(base) + s);
+    } else if (IN == IN_F32_STEREO) {
+      float2 v = __ldg(reinterpret_cast<const float2 *>(base) + s);
+      return (v.x + v.y) * 0.5f;                      // np.mean(axis=-1) in float32
+    } else if (IN == IN_I16_MONO) {
+      return (float)__ldg(reinterpret_cast<const short *>(base) + s);
+    } else {
+      short2 v = __ldg(reinterpret_cast<const short2 *>(base) + s);
+      return (float)(((int)v.x + (int)v.y) / 2);      // float64 mean cast back to int16: truncation
+    }
+  }
+};
+
+template <int IN>
+__device__ __forceinline__ const void *clip_base(const void *sig, long long off) {
+  if (IN == IN_F32_MONO) return reinterpret_cast<const float *>(sig) + off;
+  if (IN == IN_F32_STEREO) return reinterpret_cast<const float2 *>(sig) + off;
+  if (IN == IN_I16_MONO) return reinterpret_cast<const short *>(sig) + off;
+  return reinterpret_cast<const short2 *>(sig) + off;
+}
+
+// ---- the front-end kernel ----------------------------------------------------------------------
+template <int F, int IN, int MODE, int G>
+__global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams p) {
+  using C = FftCfg<F>;
+  constexpr int FPG = C::FPG, N = C::N;
+  extern __shared__ __align__(16) unsigned char smem[];
+  float *s_win = reinterpret_cast<float *>(smem + p.o_win);
+  float2 *s_tw3 = reinterpret_cast<float2 *>(smem + p.o_tw3);
+  float2 *s_pt = reinterpret_cast<float2 *>(smem + p.o_pt);
+  float *s_fbw = reinterpret_cast<float *>(smem + p.o_fbw);
+  Seg *s_segs = reinterpret_cast<Seg *>(smem + p.o_segs);
+  int *s_bseg = reinterpret_cast<int *>(smem + p.o_bseg);
+
+  for (int i = threadIdx.x; i < F; i += blockDim.x) s_win[i] = p.window[i];
+  for (int i = threadIdx.x; i < C::TW3; i += blockDim.x) s_tw3[i] = p.tw3[i];
+  for (int i = threadIdx.x; i < C::PT; i += blockDim.x) s_pt[i] = p.pt[i];
+  if (MODE == MODE_LOGFILT) {
+    for (int i = threadIdx.x; i < p.nnz; i += blockDim.x) s_fbw[i] = p.fbw[i];
+    for (int i = threadIdx.x; i < p.nseg; i += blockDim.x) s_segs[i] = p.segs[i];
+    for (int i = threadIdx.x; i <= p.num_bands; i += blockDim.x) s_bseg[i] = p.bseg[i];
+  }
+  __syncthreads();
+
+  const int g = threadIdx.x / kGroupThreads, tid = threadIdx.x % kGroupThreads;
+  unsigned char *gmem = smem + p.o_groups + (size_t)g * p.group_bytes;
+  float2 *buf1 = reinterpret_cast<float2 *>(gmem);
+  float2 *buf2 = reinterpret_cast<float2 *>(gmem + p.g_buf2);
+  float *s_partial = reinterpret_cast<float *>(gmem + p.g_partial);
+  float *s_hist = reinterpret_cast<float *>(gmem + p.g_hist);
+  float *s_lrow = reinterpret_cast<float *>(gmem + p.g_lrow);
+  float *s_red = reinterpret_cast<float *>(gmem + p.g_red);
+  volatile int *s_task = reinterpret_cast<volatile int *>(gmem + p.g_task);
+
+  // pass-2 twiddles of this thread's k1 stay in registers for the whole kernel
+  float2 tw2r[16];
+#pragma unroll
+  for (int n2 = 0; n2 < 16; ++n2) tw2r[n2] = __ldg(&p.tw2[(tid & 15) * 16 + n2]);
+
+  const int total_tasks = p.task_off[p.n_clips];
+  const int B = p.num_bands, kd = p.diff_frames;
+
+  for (;;) {
+    if (tid == 0) *s_task = atomicAdd(p.task_counter, 1);
+    group_bar(g);
+    const int task = *s_task;
+    group_bar(g);
+    if (task >= total_tasks) break;
+
+    // clip that owns this task: task_off[c] <= task < task_off[c+1]
+    int lo = 0, hi = p.n_clips;
+    while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (p.task_off[mid] <= task) lo = mid; else hi = mid;
+    }
+    const int c = lo;
+    const long long samp0 = p.clip_off[c];
+    const long long nsamp = p.clip_off[c + 1] - samp0;
+    const long long row0 = p.frame_off[c];
+    const int T = (int)(p.frame_off[c + 1] - row0);
+    const int f0 = (task - p.task_off[c]) * p.chunk;
+    const int f1 = min(T, f0 + p.chunk);
+    const int fs = (MODE == MODE_LOGFILT && kd > 0) ? max(0, f0 - kd) : f0;  // warm-up rows for the diff
+    Samples<IN> S{clip_base<IN>(p.sig, samp0)};
+
+    for (int f = fs; f < f1; f += FPG) {
+      // ---------------- pass 1: frame load * window, DFT16 ----------------
+      {
+        const int fl = (FPG > 1) ? tid / C::BPF : 0;
+        const int frame = f + fl;
+        if (frame < f1) {
+          const long long s0 = (long long)((double)frame * p.hop) - (F / 2) - p.origin;
+          float2 *b1 = buf1 + fl * C::BUF1;
+          const bool interior = (s0 >= 0) && (s0 + F <= nsamp);
+#pragma unroll 1
+          for (int it = 0; it < C::IT12; ++it) {
+            const int b = (FPG > 1) ? tid % C::BPF : tid + it * kGroupThreads;
+            if (interior) {
+              fft_pass1<F>(b, [&](int m) {
+                float2 w = *reinterpret_cast<const float2 *>(&s_win[2 * m]);
+                return make_float2(w.x * S.at(s0 + 2 * m), w.y * S.at(s0 + 2 * m + 1));
+              }, b1);
+            } else {
+              fft_pass1<F>(b, [&](int m) {
+                float2 w = *reinterpret_cast<const float2 *>(&s_win[2 * m]);
+                const long long sa = s0 + 2 * m, sb = sa + 1;
+                float xa = (sa >= 0 && sa < nsamp) ? S.at(sa) : 0.f;
+                float xb = (sb >= 0 && sb < nsamp) ? S.at(sb) : 0.f;
+                return make_float2(w.x * xa, w.y * xb);
+              }, b1);
+            }
+          }
+        }
+      }
+      group_bar(g);
+      // ---------------- pass 2: twiddle, DFT16 ----------------
+      {
+        const int fl = (FPG > 1) ? tid / C::BPF : 0;
+        if (f + fl < f1) {
+#pragma unroll 1
+          for (int it = 0; it < C::IT12; ++it) {
+            const int t2 = (FPG > 1) ? tid % C::BPF : tid + it * kGroupThreads;
+            fft_pass2<F>(t2, tw2r, buf1 + fl * C::BUF1, buf2 + fl * C::BUF2);
+          }
+        }
+      }
+      group_bar(g);
+      // ---------------- pass 3: last radix + real split (+ magnitude) ----------------
+#pragma unroll 1
+      for (int fl = 0; fl < FPG; ++fl) {
+        const int frame = f + fl;
+        if (frame >= f1) break;
+        const float2 *b2p = buf2 + fl * C::BUF2;
+        if (MODE == MODE_LOGFILT) {
+          float *mags = reinterpret_cast<float *>(buf1 + fl * C::BUF1);
+          const int kmax = p.kmax;
+          auto emit = [&](int k, float2 X) {
+            if (k < kmax) mags[k] = fast_sqrt(fmaf(X.x, X.x, X.y * X.y));
+          };
+          if (tid == 0) fft_pass3_unit0<F>(b2p, s_tw3, s_pt, emit);
+          else fft_pass3_unit<F>(tid, b2p, s_tw3, s_pt, emit);
+        } else {
+          if (frame >= f0) {
+            const long long row = row0 + frame;
+            if (p.spec_complex) {
+              float2 *o = reinterpret_cast<float2 *>(p.spec_out) + row * N;
+              auto emit = [&](int k, float2 X) { o[k] = X; };
+              if (tid == 0) fft_pass3_unit0<F>(b2p, s_tw3, s_pt, emit);
+              else fft_pass3_unit<F>(tid, b2p, s_tw3, s_pt, emit);
+            } else {
+              float *o = p.spec_out + row * N;
+              auto emit = [&](int k, float2 X) { o[k] = fast_sqrt(fmaf(X.x, X.x, X.y * X.y)); };
+              if (tid == 0) fft_pass3_unit0<F>(b2p, s_tw3, s_pt, emit);
+              else fft_pass3_unit<F>(tid, b2p, s_tw3, s_pt, emit);
+            }
+          }
+        }
+      }
+      if (MODE != MODE_LOGFILT) continue;  // next pass-1 write to buf1 is ordered by the two barriers above
+      group_bar(g);
+      // ---------------- K2a: banded filterbank, interleaved slices -> partial sums ----------------
+      {
+        const int nseg = p.nseg;
+        for (int s = tid; s < nseg; s += kGroupThreads) {
+          const Seg sg = s_segs[s];
+          float acc[FPG];
+#pragma unroll
+          for (int fl = 0; fl < FPG; ++fl) acc[fl] = 0.f;
+          int k = sg.k0, wi = sg.w0;
+          for (int i = 0; i < sg.cnt; ++i, k += sg.stride, wi += sg.stride) {
+            const float w = s_fbw[wi];
+#pragma unroll
+            for (int fl = 0; fl < FPG; ++fl)
+              acc[fl] = fmaf(w, reinterpret_cast<const float *>(buf1 + fl * C::BUF1)[k], acc[fl]);
+          }
+#pragma unroll
+          for (int fl = 0; fl < FPG; ++fl) s_partial[fl * nseg + s] = acc[fl];
+        }
+      }
+      group_bar(g);
+      // ---------------- K2b/K3: band sum, log10, lagged difference, stacked store ----------------
+      float fluxacc[FPG];
+#pragma unroll
+      for (int fl = 0; fl < FPG; ++fl) fluxacc[fl] = 0.f;
+      for (int j = tid; j < B; j += kGroupThreads) {
+        const int sb = s_bseg[j], se = s_bseg[j + 1];
+#pragma unroll
+        for (int fl = 0; fl < FPG; ++fl) {
+          const int frame = f + fl;
+          if (frame < f1) {
+            float y = 0.f;
+            for (int s = sb; s < se; ++s) y += s_partial[fl * p.nseg + s];
+            float L = p.log_enabled ? log10f(__fadd_rn(__fmul_rn(p.mul, y), p.add)) : y;
+            float D = 0.f;
+            if (kd > 0) {
+              const int slot = frame % kd;
+              const float old = s_hist[slot * B + j];
+              s_hist[slot * B + j] = L;
+              if (frame >= kd) D = L - old;
+              if (p.positive) D = fmaxf(D, 0.f);
+            }
+            if (p.num_classes > 0) s_lrow[fl * B + j] = L;
+            if (frame >= f0) {
+              const long long row = row0 + frame;
+              if (p.out != nullptr) {
+                if (p.col_spec >= 0) p.out[row * p.ld_out + p.col_spec + j] = L;
+                if (p.col_diff >= 0) p.out[row * p.ld_out + p.col_diff + j] = D;
+              }
+              fluxacc[fl] += D;
+            }
+          }
+        }
+      }
+      if (p.flux != nullptr || p.num_classes > 0) {
+        if (p.flux != nullptr) {
+#pragma unroll
+          for (int fl = 0; fl < FPG; ++fl) {
+            float v = fluxacc[fl];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+            if ((tid & 31) == 0) s_red[fl * 4 + (tid >> 5)] = v;
+          }
+        }
+        group_bar(g);
+        for (int fl = 0; fl < FPG; ++fl) {
+          const int frame = f + fl;
+          if (frame < f0 || frame >= f1) continue;
+          const long long row = row0 + frame;
+          if (p.flux != nullptr && tid == 0)
+            p.flux[row] = (s_red[fl * 4] + s_red[fl * 4 + 1]) + (s_red[fl * 4 + 2] + s_red[fl * 4 + 3]);
+          if (tid < p.num_classes) {
+            float acc = 0.f;
+            for (int i = p.proj_off[tid]; i < p.proj_off[tid + 1]; ++i)
+              acc = fmaf(__ldg(&p.proj_w[i]), s_lrow[fl * B + __ldg(&p.proj_band[i])], acc);
+            p.proj[row * p.ld_proj + tid] = acc;
+          }
+        }
+      }
+    }
+  }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace b2

@@ -1,0 +1,183 @@
+/*
+ * b200spec.h -- C ABI of libb200spec.so: the madmom-style spectral front end on B200 (sm_100a).
+ *
+ * The reference (alvaroortegaangulo/audio-tabs) has no FFI for this path: it reaches it through
+ * madmom 0.16.1's Python Processor protocol.  Each entry point below names the madmom call it
+ * replaces and the reference call site that reaches it (paths relative to /root/reference):
+ *
+ *   backend/app/services/grid/beats.py:71-75        RNNBeatProcessor()       (3 resolutions + diff)
+ *   backend/app/services/chords/extract.py:54-55    DeepChromaProcessor()    (8192 @ fps 10, 105 bands)
+ *   backend/app/services/chords/deep_chords.py:48-49,79-81                   (same; 113-band CNN chord variant)
+ *   backend/app/services/theory/key.py:99-101,143-144  CNNKeyRecognitionProcessor() (8192 @ fps 5, int16 input)
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative b200spec_status; the message is available
+ *     from b200spec_last_error() (thread-local).  No C++ exception crosses this boundary.
+ *   - the caller owns every device buffer and passes raw device pointers plus a CUDA stream handle
+ *     (void* == cudaStream_t).  The library never allocates user-visible memory and never
+ *     synchronises the stream or the device inside a compute call.
+ *   - a plan owns its device-side constants (windows, twiddles, banded filterbank, projection)
+ *     until b200spec_plan_destroy().  Host arrays passed to plan_create are copied.
+ *   - plans are immutable after creation: shareable between host threads; calls on different
+ *     streams with different workspaces are independent.
+ *   - there is no CPU fallback: on a machine without an sm_100 device plan_create fails with
+ *     B200SPEC_ERR_ARCH / B200SPEC_ERR_CUDA.
+ */
+#ifndef B200SPEC_H_
+#define B200SPEC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(B200SPEC_BUILD) && defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SPEC_ABI_VERSION 1
+#define B200SPEC_MAX_RES 4          /* resolutions per plan (RNNBeatProcessor uses 3) */
+#define B200SPEC_MAX_DIFF_FRAMES 16 /* largest supported diff lag in frames */
+
+typedef enum b200spec_status {
+  B200SPEC_OK = 0,
+  B200SPEC_ERR_ARG = -1,         /* NULL pointer, negative size, inconsistent descriptor */
+  B200SPEC_ERR_UNSUPPORTED = -2, /* frame size / option the kernels do not implement */
+  B200SPEC_ERR_CUDA = -3,        /* a CUDA runtime call failed (message has the CUDA error string) */
+  B200SPEC_ERR_ARCH = -4         /* device is not compute capability 10.x */
+} b200spec_status;
+
+/* input sample formats: madmom Signal dtype (audio/signal.py) */
+typedef enum b200spec_dtype {
+  B200SPEC_F32 = 0, /* float32 samples, window used unscaled */
+  B200SPEC_I16 = 1  /* int16 PCM, window pre-divided by 32767 (madmom stft.py: fft_window = window / iinfo.max) */
+} b200spec_dtype;
+
+/* madmom FramedSignal `end` modes (audio/signal.py FramedSignal.__init__) */
+typedef enum b200spec_end_mode {
+  B200SPEC_END_NORMAL = 0, /* num_frames = ceil(N / hop) */
+  B200SPEC_END_EXTEND = 1  /* num_frames = floor(N / hop + 1) */
+} b200spec_end_mode;
+
+/*
+ * One resolution of a plan = one madmom chain
+ *   FramedSignalProcessor -> ShortTimeFourierTransformProcessor -> FilteredSpectrogramProcessor
+ *   -> LogarithmicSpectrogramProcessor [-> SpectrogramDifferenceProcessor]
+ * The filterbank is given in banded form: band j covers FFT bins
+ *   [band_start[j], band_start[j] + band_len[j])  with weights  weights[band_woff[j] + i].
+ * (madmom's LogarithmicFilterbank is contiguous per band; the host builds it bit-identically to
+ *  madmom/audio/filters.py and passes the float32 weights through unchanged.)
+ */
+typedef struct b200spec_res_desc {
+  int32_t frame_size;        /* 1024, 2048, 4096 or 8192 (fft_size == frame_size, no Nyquist bin) */
+  double hop_size;           /* samples, may be fractional (sample_rate / fps) */
+  int32_t origin;            /* integer origin as resolved by FramedSignal (0 for 'center') */
+  const float *window;       /* host, frame_size floats: madmom's fft_window rounded to float32 */
+  int32_t num_bands;         /* B; 0 = no filterbank (stft / magnitude only) */
+  const int32_t *band_start; /* host, B */
+  const int32_t *band_len;   /* host, B */
+  const int32_t *band_woff;  /* host, B: offset of band j's first weight in `weights` */
+  const float *weights;      /* host, sum(band_len) floats */
+  int32_t log_enabled;       /* 1: out = log10(mul * y + add)  (LogarithmicSpectrogram); 0: out = y */
+  float mul, add;
+  int32_t diff_frames;       /* lag k >= 1 (madmom _diff_frames); 0 = no difference */
+  int32_t positive_diffs;    /* 1: max(diff, 0) */
+  /* optional projection of the (log-)filtered rows onto num_classes columns (chroma fold / PCP):
+   *   proj[t, c] = sum_i proj_weight[i] * L[t, proj_band[i]]  for i in [proj_off[c], proj_off[c+1]) */
+  int32_t num_classes;       /* 0 = none */
+  const int32_t *proj_off;   /* host, num_classes + 1 */
+  const int32_t *proj_band;  /* host, proj_off[num_classes] */
+  const float *proj_weight;  /* host, proj_off[num_classes] */
+} b200spec_res_desc;
+
+typedef struct b200spec_plan_desc {
+  int32_t device;   /* CUDA device ordinal */
+  int32_t dtype;    /* b200spec_dtype of the samples */
+  int32_t channels; /* 1, or 2 = interleaved stereo down-mixed on load (madmom remix: mean, cast back) */
+  int32_t num_res;  /* 1..B200SPEC_MAX_RES */
+  b200spec_res_desc res[B200SPEC_MAX_RES];
+} b200spec_plan_desc;
+
+typedef struct b200spec_plan b200spec_plan;
+
+/* where one resolution's results go inside the caller's row-major output matrices */
+typedef struct b200spec_out_desc {
+  float *d_out;      /* (total_frames, ld_out) float32, may be NULL when only flux/proj are wanted */
+  int64_t ld_out;    /* row stride in floats */
+  int32_t col_spec;  /* first column of the B (log-)filtered values, or -1 to skip */
+  int32_t col_diff;  /* first column of the B difference values, or -1 to skip (np.hstack layout) */
+  float *d_flux;     /* (total_frames,) row sums of the difference (spectral flux), or NULL */
+  float *d_proj;     /* (total_frames, ld_proj) projection output, or NULL */
+  int64_t ld_proj;
+} b200spec_out_desc;
+
+int b200spec_abi_version(void);
+const char *b200spec_last_error(void);
+
+/* madmom FramedSignal.num_frames (audio/signal.py): evaluated in float64, bit-exact with numpy. */
+int b200spec_num_frames(int64_t n_samples, double hop_size, int end_mode, int64_t *out);
+/* madmom signal_frame(): first sample index of frame `index` = int(index*hop) - frame_size/2 - origin. */
+int b200spec_frame_start(int64_t index, double hop_size, int32_t frame_size, int32_t origin, int64_t *out);
+
+int b200spec_plan_create(const b200spec_plan_desc *desc, b200spec_plan **out);
+int b200spec_plan_destroy(b200spec_plan *plan);
+
+/* bytes of device scratch a compute call on `n_clips` clips needs (pass as d_workspace). */
+size_t b200spec_workspace_bytes(int32_t n_clips);
+
+/*
+ * K1: framing + window + real FFT -> complex64 STFT.
+ * Replaces madmom.audio.stft.stft() / ShortTimeFourierTransformProcessor.process().
+ *   d_sig        samples of all clips, concatenated (interleaved if channels == 2)
+ *   d_clip_off   n_clips+1 sample offsets (per-channel sample index) of each clip in d_sig
+ *   d_frame_off  n_clips+1 row offsets of each clip's first frame in d_out
+ *   total_frames d_frame_off[n_clips] (host copy, sizes the grid)
+ *   d_out        (total_frames, frame_size/2) complex64 as interleaved float pairs
+ */
+int b200spec_stft(const b200spec_plan *plan, int32_t res, const void *d_sig, const int64_t *d_clip_off,
+                  const int64_t *d_frame_off, int32_t n_clips, int64_t total_frames, float *d_out,
+                  void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* K1 + |.|: magnitude spectrogram (madmom Spectrogram = np.abs(stft)); d_out is (total_frames, frame_size/2) float32. */
+int b200spec_spectrogram(const b200spec_plan *plan, int32_t res, const void *d_sig, const int64_t *d_clip_off,
+                         const int64_t *d_frame_off, int32_t n_clips, int64_t total_frames, float *d_out,
+                         void *d_workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * K1 + K2 + K3 fused: frames -> window -> FFT -> magnitude -> banded filterbank -> log10(mul*y+add)
+ * -> lagged (positive) difference -> optional flux / projection, written straight into the
+ * caller's stacked layout.  Replaces the whole madmom chain named above for resolution `res`.
+ */
+int b200spec_logfilt(const b200spec_plan *plan, int32_t res, const void *d_sig, const int64_t *d_clip_off,
+                     const int64_t *d_frame_off, int32_t n_clips, int64_t total_frames,
+                     const b200spec_out_desc *out, void *d_workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * Stand-alone stages on caller-supplied matrices (used when a madmom chain is not fusable,
+ * e.g. SpectrogramDifferenceProcessor applied to an arbitrary array):
+ *   magnitude   np.abs(complex64)                       madmom Spectrogram
+ *   filter_log  np.dot(spec, fb) [+ log10(mul*y+add)]   madmom FilteredSpectrogram / LogarithmicSpectrogram
+ *   diff        lagged difference per clip              madmom SpectrogramDifference(+Processor NaN-pad => first k rows 0)
+ */
+int b200spec_magnitude(const float *d_stft, int64_t n_elems, float *d_out, void *stream);
+int b200spec_filter_log(const b200spec_plan *plan, int32_t res, const float *d_spec, int64_t ld_spec,
+                        int64_t total_frames, int32_t apply_filter, int32_t apply_log, float *d_out,
+                        int64_t ld_out, void *stream);
+int b200spec_diff_flux_chroma(const b200spec_plan *plan, int32_t res, const float *d_L, int64_t ld_L,
+                              const int64_t *d_frame_off, int32_t n_clips, int64_t total_frames,
+                              const b200spec_out_desc *out, void *stream);
+
+/* introspection used by tests and the host layer */
+int b200spec_plan_num_res(const b200spec_plan *plan);
+int b200spec_plan_num_bands(const b200spec_plan *plan, int32_t res);
+/* number of kernel launches the library has issued in this process (bench.py's gpu_launches) */
+int64_t b200spec_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#if defined(B200SPEC_BUILD) && defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#endif /* B200SPEC_H_ */

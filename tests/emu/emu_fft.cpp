@@ -1,0 +1,76 @@
+// CPU emulation of the thread-mapped FFT passes in audio_tabs_b200/csrc/fft_core.cuh.
+// Test infrastructure only: runs every "thread" of every pass sequentially and compares the
+// resulting half spectrum with a naive float64 DFT of the windowed frame.
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+#include <complex>
+#include "../../audio_tabs_b200/csrc/fft_core.cuh"
+
+template <int F>
+double run_one(unsigned seed) {
+  using C = b2::FftCfg<F>;
+  const double PI = 3.14159265358979323846;
+  std::vector<float> x(F), w(F);
+  srand(seed);
+  for (int i = 0; i < F; ++i) {
+    x[i] = (float)rand() / RAND_MAX * 2.f - 1.f;
+    w[i] = (float)(0.5 * (0.5 - 0.5 * cos(2 * PI * i / (F - 1))));  // hanning * 1/2
+  }
+  std::vector<float2> tw2(16 * 16), tw3(C::TW3), pt(C::PT);
+  for (int k1 = 0; k1 < 16; ++k1)
+    for (int n2 = 0; n2 < 16; ++n2) {
+      double a = -2 * PI * (n2 * k1) / 256.0;
+      tw2[k1 * 16 + n2] = make_float2((float)cos(a), (float)sin(a));
+    }
+  for (int q = 0; q <= 128; ++q)
+    for (int n3 = 0; n3 < C::R3; ++n3) {
+      double a = -2 * PI * ((double)n3 * q) / C::N;
+      tw3[q * C::R3 + n3] = make_float2((float)cos(a), (float)sin(a));
+    }
+  for (int k3 = 0; k3 < C::R3; ++k3)
+    for (int q = 0; q <= 128; ++q) {
+      double a = -2 * PI * (q + 256.0 * k3) / F;
+      // -i * W = -i (cos a + i sin a) = sin a - i cos a
+      pt[k3 * 129 + q] = make_float2((float)sin(a), (float)-cos(a));
+    }
+  std::vector<float2> buf1(C::BUF1), buf2(C::BUF2), X(C::N);
+  std::vector<int> hits(C::N, 0);
+  auto load = [&](int m) { return make_float2(w[2 * m] * x[2 * m], w[2 * m + 1] * x[2 * m + 1]); };
+  for (int b = 0; b < C::BPF; ++b) b2::fft_pass1<F>(b, load, buf1.data());
+  for (int t2 = 0; t2 < C::BPF; ++t2) {
+    float2 t[16];
+    for (int n2 = 0; n2 < 16; ++n2) t[n2] = tw2[(t2 & 15) * 16 + n2];
+    b2::fft_pass2<F>(t2, t, buf1.data(), buf2.data());
+  }
+  auto emit = [&](int k, float2 v) { X[k] = v; hits[k]++; };
+  b2::fft_pass3_unit0<F>(buf2.data(), tw3.data(), pt.data(), emit);
+  for (int u = 1; u < 128; ++u) b2::fft_pass3_unit<F>(u, buf2.data(), tw3.data(), pt.data(), emit);
+  // reference
+  double maxerr = 0, peak = 0;
+  for (int k = 0; k < C::N; ++k) {
+    if (hits[k] != 1) { printf("F=%d bin %d emitted %d times\n", F, k, hits[k]); return 1e9; }
+    std::complex<double> s = 0;
+    for (int n = 0; n < F; ++n) {
+      double a = -2 * PI * ((double)((long long)n * k % F)) / F;
+      s += 2.0 * (double)w[n] * (double)x[n] * std::complex<double>(cos(a), sin(a));
+    }
+    double e = std::abs(s - std::complex<double>(X[k].x, X[k].y));
+    if (e > maxerr) maxerr = e;
+    if (std::abs(s) > peak) peak = std::abs(s);
+  }
+  printf("F=%d max abs err %.3e, peak %.3e, rel-to-peak %.3e\n", F, maxerr, peak, maxerr / peak);
+  return maxerr / peak;
+}
+
+int main() {
+  double e = 0;
+  e = fmax(e, run_one<1024>(1));
+  e = fmax(e, run_one<2048>(2));
+  e = fmax(e, run_one<4096>(3));
+  e = fmax(e, run_one<8192>(4));
+  if (e > 2e-6) { printf("FAIL\n"); return 1; }
+  printf("OK\n");
+  return 0;
+}
