@@ -1,0 +1,271 @@
+"""Spectrogram family (madmom 0.16.1 ``madmom/audio/spectrogram.py``) on the fused CUDA kernels.
+
+Classes and processors keep madmom's constructor keywords, defaults, attributes and exception
+types.  The reference reaches them through RNNBeatProcessor
+(/root/reference/backend/app/services/grid/beats.py:74), DeepChromaProcessor
+(chords/extract.py:54, chords/deep_chords.py:48) and CNNKeyRecognitionProcessor (theory/key.py:101).
+All stages are lazy (see lazy.py): materialising the last stage of an intact chain runs
+framing+window+FFT+magnitude+filterbank+log10+difference in one kernel.
+"""
+from __future__ import annotations
+
+import inspect
+
+import numpy as np
+
+from ..filters import (A4, FMAX, FMIN, NORM_FILTERS, NUM_BANDS, UNIQUE_FILTERS, Filterbank,
+                       LogarithmicFilterbank)
+from ..processors import Processor
+from .lazy import LazyArray
+from .stft import ShortTimeFourierTransform
+
+MUL, ADD, LOG = 1.0, 1.0, np.log10
+DIFF_RATIO, DIFF_FRAMES, DIFF_MAX_BINS, POSITIVE_DIFFS = 0.5, None, None, False
+
+
+class _Stage(LazyArray):
+    """Common attribute plumbing: every stage exposes ``stft``, ``frames`` and ``bin_frequencies``."""
+    stft = None
+    source = None          # upstream stage (LazyArray) or a plain ndarray
+
+    @property
+    def frames(self):
+        return self.stft.frames if self.stft is not None else None
+
+    @property
+    def num_frames(self):
+        return self.shape[0]
+
+    @property
+    def num_bins(self):
+        return self.shape[1]
+
+    def _compute_tensor(self):
+        from ..engine import run_chain
+        return run_chain(self)
+
+
+class Spectrogram(_Stage):
+    """np.abs(stft) (madmom Spectrogram)."""
+
+    def __init__(self, stft, **kwargs):
+        if isinstance(stft, Spectrogram):
+            self.__dict__.update(stft.__dict__)
+            return
+        if isinstance(stft, np.ndarray) and not np.iscomplexobj(stft) and stft.ndim == 2:
+            # already a magnitude spectrogram held on the host
+            self.stft, self.source = None, np.ascontiguousarray(stft, dtype=np.float32)
+            self.bin_frequencies = kwargs.get("bin_frequencies", np.arange(stft.shape[1], dtype=float))
+            return
+        if not isinstance(stft, ShortTimeFourierTransform):
+            stft = ShortTimeFourierTransform(stft, **kwargs)
+        self.stft = stft
+        self.source = stft
+        self.bin_frequencies = stft.bin_frequencies
+
+    def _result_shape(self):
+        return self.source.shape
+
+    def diff(self, **kwargs):
+        return SpectrogramDifference(self, **kwargs)
+
+    def filter(self, **kwargs):
+        return FilteredSpectrogram(self, **kwargs)
+
+    def log(self, **kwargs):
+        return LogarithmicSpectrogram(self, **kwargs)
+
+
+class SpectrogramProcessor(Processor):
+    def __init__(self, **kwargs):
+        pass
+
+    def process(self, data, **kwargs):
+        return Spectrogram(data, **kwargs)
+
+
+def _as_spectrogram(data, **kwargs):
+    if isinstance(data, _Stage):
+        return data
+    return Spectrogram(data, **kwargs)
+
+
+class FilteredSpectrogram(_Stage):
+    """np.dot(spec, filterbank) (madmom FilteredSpectrogram)."""
+
+    def __init__(self, spectrogram, filterbank=LogarithmicFilterbank, num_bands=NUM_BANDS, fmin=FMIN,
+                 fmax=FMAX, fref=A4, norm_filters=NORM_FILTERS, unique_filters=UNIQUE_FILTERS, **kwargs):
+        spectrogram = _as_spectrogram(spectrogram, **kwargs)
+        if inspect.isclass(filterbank) and issubclass(filterbank, Filterbank):
+            filterbank = filterbank(spectrogram.bin_frequencies, num_bands=num_bands, fmin=fmin, fmax=fmax,
+                                    fref=fref, norm_filters=norm_filters, unique_filters=unique_filters)
+        if not isinstance(filterbank, Filterbank):
+            raise TypeError("not a Filterbank type or instance: %s" % filterbank)
+        if filterbank.shape[0] != spectrogram.shape[1]:
+            raise ValueError("filterbank has %d bins, spectrogram %d" % (filterbank.shape[0], spectrogram.shape[1]))
+        self.source = spectrogram
+        self.stft = spectrogram.stft
+        self.filterbank = filterbank
+        self.bin_frequencies = filterbank.center_frequencies
+
+    def _result_shape(self):
+        return (self.source.shape[0], self.filterbank.shape[1])
+
+
+class FilteredSpectrogramProcessor(Processor):
+    def __init__(self, filterbank=LogarithmicFilterbank, num_bands=NUM_BANDS, fmin=FMIN, fmax=FMAX, fref=A4,
+                 norm_filters=NORM_FILTERS, unique_filters=UNIQUE_FILTERS, **kwargs):
+        self.filterbank = filterbank
+        self.num_bands, self.fmin, self.fmax, self.fref = num_bands, fmin, fmax, fref
+        self.norm_filters, self.unique_filters = norm_filters, unique_filters
+
+    def process(self, data, **kwargs):
+        args = dict(filterbank=self.filterbank, num_bands=self.num_bands, fmin=self.fmin, fmax=self.fmax,
+                    fref=self.fref, norm_filters=self.norm_filters, unique_filters=self.unique_filters)
+        args.update(kwargs)
+        out = FilteredSpectrogram(data, **args)
+        self.filterbank = out.filterbank        # cache the built filterbank, like madmom
+        return out
+
+
+class LogarithmicSpectrogram(_Stage):
+    """log10(mul * spec + add) (madmom LogarithmicSpectrogram); only np.log10 runs on the device."""
+
+    def __init__(self, spectrogram, log=LOG, mul=MUL, add=ADD, **kwargs):
+        spectrogram = _as_spectrogram(spectrogram, **kwargs)
+        if log is not np.log10:
+            raise ValueError("only log=np.log10 is implemented on the device (madmom's default)")
+        self.source = spectrogram
+        self.stft = spectrogram.stft
+        self.filterbank = getattr(spectrogram, "filterbank", None)
+        self.bin_frequencies = spectrogram.bin_frequencies
+        self.mul, self.add = mul, add
+
+    def _result_shape(self):
+        return self.source.shape
+
+
+class LogarithmicSpectrogramProcessor(Processor):
+    def __init__(self, log=LOG, mul=MUL, add=ADD, **kwargs):
+        self.log, self.mul, self.add = log, mul, add
+
+    def process(self, data, **kwargs):
+        args = dict(log=self.log, mul=self.mul, add=self.add)
+        args.update(kwargs)
+        return LogarithmicSpectrogram(data, **args)
+
+
+class LogarithmicFilteredSpectrogram(LogarithmicSpectrogram):
+    def __init__(self, spectrogram, filterbank=LogarithmicFilterbank, num_bands=NUM_BANDS, fmin=FMIN, fmax=FMAX,
+                 fref=A4, norm_filters=NORM_FILTERS, unique_filters=UNIQUE_FILTERS, mul=MUL, add=ADD, **kwargs):
+        if not isinstance(spectrogram, FilteredSpectrogram):
+            spectrogram = FilteredSpectrogram(spectrogram, filterbank=filterbank, num_bands=num_bands, fmin=fmin,
+                                              fmax=fmax, fref=fref, norm_filters=norm_filters,
+                                              unique_filters=unique_filters, **kwargs)
+        LogarithmicSpectrogram.__init__(self, spectrogram, mul=mul, add=add)
+
+
+class LogarithmicFilteredSpectrogramProcessor(Processor):
+    def __init__(self, filterbank=LogarithmicFilterbank, num_bands=NUM_BANDS, fmin=FMIN, fmax=FMAX, fref=A4,
+                 norm_filters=NORM_FILTERS, unique_filters=UNIQUE_FILTERS, mul=MUL, add=ADD, **kwargs):
+        self.filterbank = filterbank
+        self.num_bands, self.fmin, self.fmax, self.fref = num_bands, fmin, fmax, fref
+        self.norm_filters, self.unique_filters = norm_filters, unique_filters
+        self.mul, self.add = mul, add
+
+    def process(self, data, **kwargs):
+        args = dict(filterbank=self.filterbank, num_bands=self.num_bands, fmin=self.fmin, fmax=self.fmax,
+                    fref=self.fref, norm_filters=self.norm_filters, unique_filters=self.unique_filters,
+                    mul=self.mul, add=self.add)
+        args.update(kwargs)
+        out = LogarithmicFilteredSpectrogram(data, **args)
+        self.filterbank = out.filterbank
+        return out
+
+
+def _diff_frames(diff_ratio, hop_size, frame_size, window=np.hanning):
+    """madmom.audio.spectrogram._diff_frames (host-side integer geometry, bit-exact)."""
+    if hasattr(window, "__call__"):
+        window = window(frame_size)
+    sample = np.argmax(window > float(diff_ratio) * max(window))
+    diff_samples = len(window) / 2 - sample
+    return int(max(1, round(diff_samples / hop_size)))
+
+
+class SpectrogramDifference(_Stage):
+    """Lagged (positive) first-order difference (madmom SpectrogramDifference)."""
+
+    def __init__(self, spectrogram, diff_ratio=DIFF_RATIO, diff_frames=DIFF_FRAMES, diff_max_bins=DIFF_MAX_BINS,
+                 positive_diffs=POSITIVE_DIFFS, keep_dims=True, **kwargs):
+        spectrogram = _as_spectrogram(spectrogram, **kwargs)
+        if diff_frames is None:
+            diff_frames = _diff_frames(diff_ratio, frame_size=spectrogram.stft.frames.frame_size,
+                                       hop_size=spectrogram.stft.frames.hop_size, window=spectrogram.stft.window)
+        if diff_frames < 1:
+            raise ValueError("number of `diff_frames` must be >= 1")
+        if diff_max_bins is not None and diff_max_bins > 1:
+            raise ValueError("diff_max_bins > 1 (SuperFlux maximum filter) is not implemented on the device")
+        self.source = spectrogram
+        self.spectrogram = spectrogram
+        self.stft = spectrogram.stft
+        self.filterbank = getattr(spectrogram, "filterbank", None)
+        self.bin_frequencies = spectrogram.bin_frequencies
+        self.diff_ratio, self.diff_frames, self.diff_max_bins = diff_ratio, int(diff_frames), diff_max_bins
+        self.positive_diffs = positive_diffs
+
+    def _result_shape(self):
+        return self.source.shape
+
+    def positive_diff(self):
+        return np.maximum(np.asarray(self), 0)
+
+
+class StackedDifference(_Stage):
+    """``np.hstack((spec, diff))`` produced directly by the fused kernel."""
+
+    def __init__(self, diff):
+        self.source = diff
+        self.stft = diff.stft
+        self.diff = diff
+        self.bin_frequencies = diff.bin_frequencies
+
+    def _result_shape(self):
+        t, b = self.source.shape
+        return (t, 2 * b)
+
+
+class SpectrogramDifferenceProcessor(Processor):
+    """Offline behaviour of madmom's processor (``reset=True``): the first ``diff_frames`` rows are 0."""
+
+    def __init__(self, diff_ratio=DIFF_RATIO, diff_frames=DIFF_FRAMES, diff_max_bins=DIFF_MAX_BINS,
+                 positive_diffs=POSITIVE_DIFFS, stack_diffs=None, **kwargs):
+        self.diff_ratio, self.diff_frames, self.diff_max_bins = diff_ratio, diff_frames, diff_max_bins
+        self.positive_diffs, self.stack_diffs = positive_diffs, stack_diffs
+        self._buffer = None
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state.pop("_buffer", None)
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self._buffer = None
+
+    def process(self, data, reset=True, **kwargs):
+        if not reset:
+            raise ValueError("online mode (reset=False) is not implemented on the device")
+        args = dict(diff_ratio=self.diff_ratio, diff_frames=self.diff_frames, diff_max_bins=self.diff_max_bins,
+                    positive_diffs=self.positive_diffs)
+        args.update(kwargs)
+        data = _as_spectrogram(data)
+        if self.diff_frames is None:
+            self.diff_frames = _diff_frames(args["diff_ratio"], frame_size=data.stft.frames.frame_size,
+                                            hop_size=data.stft.frames.hop_size, window=data.stft.window)
+            args["diff_frames"] = self.diff_frames
+        diff = SpectrogramDifference(data, **args)
+        if self.stack_diffs is None:
+            return diff
+        if self.stack_diffs is np.hstack:
+            return StackedDifference(diff)
+        return self.stack_diffs((np.asarray(data), np.asarray(diff)))

@@ -1,0 +1,373 @@
+"""Plans and the batch engine: host-side layer between the madmom-shaped processors and the C ABI.
+
+A ``ResolutionSpec`` describes one madmom chain (FramedSignalProcessor -> STFT -> filterbank -> log
+-> difference).  ``get_plan`` caches device plans the way madmom's processors cache ``fft_window``
+and ``filterbank``.  ``FrontEnd`` runs batches of clips through the fused kernels, either on
+device-resident packed input (``run_packed``) or from host arrays with pinned, stream-overlapped
+copies (``process_batch``).
+
+PyTorch is used for device memory, streams and events only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import hashlib
+import threading
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _ffi
+from .filters import Filterbank
+
+SUPPORTED_FRAME_SIZES = (1024, 2048, 4096, 8192)
+
+
+def _digest(*arrays) -> str:
+    h = hashlib.sha1()
+    for a in arrays:
+        if a is None:
+            h.update(b"-")
+        else:
+            a = np.ascontiguousarray(a)
+            h.update(str(a.dtype).encode())
+            h.update(str(a.shape).encode())
+            h.update(a.tobytes())
+    return h.hexdigest()
+
+
+@dataclass
+class ResolutionSpec:
+    frame_size: int
+    hop_size: float = 441.0
+    origin: int = 0
+    fft_window: Optional[np.ndarray] = None     # float64/32, length frame_size (madmom's fft_window)
+    filterbank: Optional[Filterbank] = None     # None -> STFT / magnitude only
+    log: bool = True
+    mul: float = 1.0
+    add: float = 1.0
+    diff_frames: int = 0
+    positive_diffs: bool = False
+    proj_classes: Optional[np.ndarray] = None   # per band class index (or -1), e.g. chroma fold
+    proj_matrix: Optional[np.ndarray] = None    # or a dense (B, C) projection
+    num_classes: int = 0
+    _key: str = field(default="", repr=False)
+
+    def __post_init__(self):
+        self.frame_size = int(self.frame_size)
+        self.hop_size = float(self.hop_size)
+        self.origin = int(self.origin)
+        if self.fft_window is None:
+            self.fft_window = np.hanning(self.frame_size)
+        win = np.asarray(self.fft_window)
+        if win.shape != (self.frame_size,):
+            raise ValueError("window must have frame_size elements")
+        self.window32 = np.ascontiguousarray(win, dtype=np.float32)
+        if self.filterbank is not None and not isinstance(self.filterbank, Filterbank):
+            raise TypeError("not a Filterbank type or instance: %s" % self.filterbank)
+        if self.filterbank is not None and self.filterbank.shape[0] != self.frame_size // 2:
+            raise ValueError("filterbank must have frame_size/2 bins")
+        self.num_bands = 0 if self.filterbank is None else int(self.filterbank.shape[1])
+        # projection in CSR-by-class form
+        self.proj_off = self.proj_band = self.proj_weight = None
+        if self.proj_classes is not None:
+            cls = np.asarray(self.proj_classes, dtype=np.int64)
+            C_ = int(self.num_classes or (cls.max() + 1))
+            order = [np.nonzero(cls == c)[0] for c in range(C_)]
+            self.num_classes = C_
+            self.proj_off = np.concatenate(([0], np.cumsum([len(o) for o in order]))).astype(np.int32)
+            self.proj_band = (np.concatenate(order) if order else np.zeros(0)).astype(np.int32)
+            self.proj_weight = np.ones(len(self.proj_band), np.float32)
+        elif self.proj_matrix is not None:
+            P = np.asarray(self.proj_matrix, dtype=np.float32)
+            if P.shape[0] != self.num_bands:
+                raise ValueError("projection must have num_bands rows")
+            self.num_classes = P.shape[1]
+            bands = [np.nonzero(P[:, c])[0] for c in range(P.shape[1])]
+            self.proj_off = np.concatenate(([0], np.cumsum([len(b) for b in bands]))).astype(np.int32)
+            self.proj_band = (np.concatenate(bands) if bands else np.zeros(0)).astype(np.int32)
+            self.proj_weight = np.concatenate([P[b, c] for c, b in enumerate(bands)]).astype(np.float32) \
+                if bands else np.zeros(0, np.float32)
+        self._key = "|".join(map(str, (
+            self.frame_size, repr(self.hop_size), self.origin, _digest(self.window32),
+            _digest(None if self.filterbank is None else np.asarray(self.filterbank)),
+            int(self.log), repr(float(self.mul)), repr(float(self.add)), self.diff_frames,
+            int(self.positive_diffs), _digest(self.proj_off, self.proj_band, self.proj_weight))))
+
+    @property
+    def num_bins(self):
+        return self.frame_size // 2
+
+    @property
+    def out_width(self):
+        """columns this resolution contributes to a stacked output: [spec | diff]"""
+        return self.num_bands * (2 if self.diff_frames > 0 else 1)
+
+
+class DevicePlan:
+    """Owns one b200spec_plan (device constants for up to 4 resolutions)."""
+
+    def __init__(self, device: int, dtype: str, channels: int, specs: Sequence[ResolutionSpec]):
+        if len(specs) < 1 or len(specs) > _ffi.MAX_RES:
+            raise ValueError("a plan holds 1..%d resolutions" % _ffi.MAX_RES)
+        self.device, self.dtype, self.channels, self.specs = int(device), dtype, int(channels), list(specs)
+        lib = _ffi.lib()
+        desc = _ffi.PlanDesc()
+        desc.device = self.device
+        desc.dtype = {"f32": _ffi.F32, "i16": _ffi.I16}[dtype]
+        desc.channels = self.channels
+        desc.num_res = len(specs)
+        keep = []
+
+        def fptr(a):
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            keep.append(a)
+            return a.ctypes.data_as(_ffi.c_float_p)
+
+        def iptr(a):
+            a = np.ascontiguousarray(a, dtype=np.int32)
+            keep.append(a)
+            return a.ctypes.data_as(_ffi.c_int32_p)
+
+        for i, s in enumerate(specs):
+            r = desc.res[i]
+            r.frame_size, r.hop_size, r.origin = s.frame_size, s.hop_size, s.origin
+            r.window = fptr(s.window32)
+            r.num_bands = s.num_bands
+            if s.filterbank is not None:
+                start, length, woff, weights = s.filterbank.banded()
+                r.band_start, r.band_len, r.band_woff, r.weights = iptr(start), iptr(length), iptr(woff), fptr(weights)
+            r.log_enabled = int(bool(s.log))
+            r.mul, r.add = float(s.mul), float(s.add)
+            r.diff_frames, r.positive_diffs = int(s.diff_frames), int(bool(s.positive_diffs))
+            r.num_classes = int(s.num_classes) if s.proj_off is not None else 0
+            if s.proj_off is not None:
+                r.proj_off, r.proj_band, r.proj_weight = iptr(s.proj_off), iptr(s.proj_band), fptr(s.proj_weight)
+        handle = C.c_void_p()
+        _ffi.check(lib.b200spec_plan_create(C.byref(desc), C.byref(handle)))
+        self._handle = handle
+        self._lib = lib
+
+    @property
+    def handle(self):
+        return self._handle
+
+    def close(self):
+        if getattr(self, "_handle", None):
+            self._lib.b200spec_plan_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):  # pragma: no cover - best effort
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_PLAN_CACHE = {}
+_PLAN_LOCK = threading.Lock()
+
+
+def get_plan(device: int, dtype: str, channels: int, specs: Sequence[ResolutionSpec]) -> DevicePlan:
+    key = (int(device), dtype, int(channels), tuple(s._key for s in specs))
+    with _PLAN_LOCK:
+        plan = _PLAN_CACHE.get(key)
+        if plan is None:
+            plan = DevicePlan(device, dtype, channels, specs)
+            _PLAN_CACHE[key] = plan
+        return plan
+
+
+def clear_plan_cache():
+    with _PLAN_LOCK:
+        for p in _PLAN_CACHE.values():
+            p.close()
+        _PLAN_CACHE.clear()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream_ptr(stream: Optional[torch.cuda.Stream], device) -> C.c_void_p:
+    s = stream if stream is not None else torch.cuda.current_stream(device)
+    return C.c_void_p(s.cuda_stream)
+
+
+def require_cuda(device: int = 0) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("audio_tabs_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", device)
+
+
+def dtype_name(dt) -> str:
+    dt = np.dtype(dt) if not isinstance(dt, torch.dtype) else dt
+    if dt in (np.dtype(np.float32), torch.float32):
+        return "f32"
+    if dt in (np.dtype(np.int16), torch.int16):
+        return "i16"
+    raise ValueError("only float32 and int16 signals are supported on the device (got %s)" % dt)
+
+
+class Packed:
+    """A batch of clips packed back to back on the device, with per-clip sample/row offsets."""
+
+    def __init__(self, sig: torch.Tensor, lengths: Sequence[int], hop_size: float, end: str = "normal",
+                 num_frames: Optional[Sequence[int]] = None):
+        self.sig = sig
+        self.lengths = [int(n) for n in lengths]
+        self.n_clips = len(self.lengths)
+        if num_frames is None:
+            num_frames = [_ffi.num_frames(n, hop_size, end) for n in self.lengths]
+        self.num_frames = [int(t) for t in num_frames]
+        clip_off = np.zeros(self.n_clips + 1, np.int64)
+        np.cumsum(self.lengths, out=clip_off[1:])
+        frame_off = np.zeros(self.n_clips + 1, np.int64)
+        np.cumsum(self.num_frames, out=frame_off[1:])
+        self.clip_off_host, self.frame_off_host = clip_off, frame_off
+        self.total_frames = int(frame_off[-1])
+        dev = sig.device
+        self.clip_off = torch.from_numpy(clip_off).to(dev)
+        self.frame_off = torch.from_numpy(frame_off).to(dev)
+
+
+class FrontEnd:
+    """Fused multi-resolution front end for one device.
+
+    Output layout per frame row: for every resolution in order ``[spec_r | diff_r]`` (the
+    ``np.hstack`` order of madmom's RNNBeatProcessor pre-processor); optional flux / projection
+    outputs are separate matrices.
+    """
+
+    def __init__(self, specs: Sequence[ResolutionSpec], device: int = 0, dtype: str = "f32", channels: int = 1,
+                 end: str = "normal", concurrent_streams: bool = True):
+        self.specs = list(specs)
+        hops = {s.hop_size for s in self.specs}
+        if len(hops) != 1:
+            raise ValueError("all resolutions of a FrontEnd must share hop_size (rows are stacked per frame)")
+        self.hop_size = self.specs[0].hop_size
+        self.end = end
+        self.device = require_cuda(device)
+        self.dtype, self.channels = dtype, int(channels)
+        self.plan = get_plan(device, dtype, channels, self.specs)
+        self.col = []
+        c = 0
+        for s in self.specs:
+            self.col.append(c)
+            c += s.out_width
+        self.width = c
+        self._lib = _ffi.lib()
+        self._workspaces = {}
+        self._streams = None
+        self._events = None
+        self.concurrent_streams = concurrent_streams and len(self.specs) > 1
+
+    # ---- helpers ---------------------------------------------------------------------------
+    def _workspace(self, res: int, n_clips: int) -> torch.Tensor:
+        need = int(self._lib.b200spec_workspace_bytes(n_clips))
+        ws = self._workspaces.get(res)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(max(need, 4096), dtype=torch.uint8, device=self.device)
+            self._workspaces[res] = ws
+        return ws
+
+    def _side_streams(self):
+        if self._streams is None:
+            self._streams = [torch.cuda.Stream(self.device) for _ in self.specs[1:]]
+            self._events = [torch.cuda.Event() for _ in self.specs]
+        return self._streams
+
+    def torch_dtype(self):
+        return torch.float32 if self.dtype == "f32" else torch.int16
+
+    def pack(self, signals: Sequence, non_blocking: bool = True) -> Packed:
+        """Copy a list of host arrays / tensors into one packed device buffer."""
+        tdt = self.torch_dtype()
+        lens = [int(s.shape[0]) for s in signals]
+        ch = self.channels
+        total = sum(lens)
+        shape = (total,) if ch == 1 else (total, ch)
+        sig = torch.empty(shape, dtype=tdt, device=self.device)
+        o = 0
+        for s, n in zip(signals, lens):
+            t = s if isinstance(s, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(s))
+            if t.dtype != tdt:
+                raise ValueError("signal dtype %s does not match the plan dtype %s" % (t.dtype, tdt))
+            if (t.ndim == 2) != (ch == 2) or (t.ndim == 2 and t.shape[1] != ch):
+                raise ValueError("signal shape %s does not match channels=%d" % (tuple(t.shape), ch))
+            sig[o:o + n].copy_(t, non_blocking=non_blocking)
+            o += n
+        return Packed(sig, lens, self.hop_size, self.end)
+
+    def alloc_output(self, total_frames: int) -> torch.Tensor:
+        return torch.empty((total_frames, self.width), dtype=torch.float32, device=self.device)
+
+    # ---- device-resident hot path ----------------------------------------------------------
+    def run_packed(self, packed: Packed, out: Optional[torch.Tensor] = None, flux: Optional[List] = None,
+                   proj: Optional[List] = None) -> torch.Tensor:
+        """Launch the fused kernels for every resolution; returns the stacked (rows, width) tensor.
+
+        ``out=False`` skips the stacked matrix (only ``flux`` / ``proj`` are written).
+        No synchronisation: results are ordered on the current stream.
+        """
+        if out is None:
+            out = self.alloc_output(packed.total_frames)
+        if out is not False and (out.shape != (packed.total_frames, self.width) or out.dtype != torch.float32
+                                 or not out.is_contiguous()):
+            raise ValueError("out must be a contiguous float32 (total_frames, %d) tensor" % self.width)
+        cur = torch.cuda.current_stream(self.device)
+        use_side = self.concurrent_streams and packed.total_frames > 0
+        side = self._side_streams() if use_side else None
+        if use_side:
+            self._events[0].record(cur)
+        for r, s in enumerate(self.specs):
+            stream = cur
+            if use_side and r > 0:
+                stream = side[r - 1]
+                stream.wait_event(self._events[0])
+            od = _ffi.OutDesc()
+            od.d_out = out.data_ptr() if out is not False else None
+            od.ld_out = self.width
+            od.col_spec = self.col[r]
+            od.col_diff = self.col[r] + s.num_bands if s.diff_frames > 0 else -1
+            od.d_flux = flux[r].data_ptr() if flux is not None and flux[r] is not None else None
+            od.d_proj = proj[r].data_ptr() if proj is not None and proj[r] is not None else None
+            od.ld_proj = proj[r].shape[1] if proj is not None and proj[r] is not None else 0
+            ws = self._workspace(r, packed.n_clips)
+            _ffi.check(self._lib.b200spec_logfilt(
+                self.plan.handle, r, _ptr(packed.sig), _ptr(packed.clip_off), _ptr(packed.frame_off),
+                packed.n_clips, packed.total_frames, C.byref(od), _ptr(ws), ws.numel(),
+                C.c_void_p(stream.cuda_stream)))
+            if use_side and r > 0:
+                self._events[r].record(stream)
+                cur.wait_event(self._events[r])
+        return out
+
+    def stft_packed(self, packed: Packed, res: int = 0, complex_out: bool = True) -> torch.Tensor:
+        s = self.specs[res]
+        if complex_out:
+            out = torch.empty((packed.total_frames, s.num_bins), dtype=torch.complex64, device=self.device)
+            fn = self._lib.b200spec_stft
+        else:
+            out = torch.empty((packed.total_frames, s.num_bins), dtype=torch.float32, device=self.device)
+            fn = self._lib.b200spec_spectrogram
+        ws = self._workspace(res, packed.n_clips)
+        _ffi.check(fn(self.plan.handle, res, _ptr(packed.sig), _ptr(packed.clip_off), _ptr(packed.frame_off),
+                      packed.n_clips, packed.total_frames, _ptr(out), _ptr(ws), ws.numel(),
+                      _stream_ptr(None, self.device)))
+        return out
+
+    # ---- host in / host out ----------------------------------------------------------------
+    def process_batch(self, signals: Sequence, return_tensors: bool = False):
+        """signals: list of host arrays (float32 / int16; (N,) or (N, 2)). Returns one (T_i, width) per clip."""
+        packed = self.pack(signals)
+        out = self.run_packed(packed)
+        if return_tensors:
+            return [out[packed.frame_off_host[i]:packed.frame_off_host[i + 1]] for i in range(packed.n_clips)]
+        host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+        host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        arr = host.numpy()
+        return [arr[packed.frame_off_host[i]:packed.frame_off_host[i + 1]] for i in range(packed.n_clips)]
