@@ -242,7 +242,7 @@ class FrontEnd:
     """
 
     def __init__(self, specs: Sequence[ResolutionSpec], device: int = 0, dtype: str = "f32", channels: int = 1,
-                 end: str = "normal", concurrent_streams: bool = True):
+                 end: str = "normal", concurrent_streams: bool = False):
         self.specs = list(specs)
         hops = {s.hop_size for s in self.specs}
         if len(hops) != 1:
@@ -358,6 +358,79 @@ class FrontEnd:
                       packed.n_clips, packed.total_frames, _ptr(out), _ptr(ws), ws.numel(),
                       _stream_ptr(None, self.device)))
         return out
+
+    # ---- pinned host in / pinned host out, copies overlapped with compute ----------------------
+    def _pipeline(self, lengths, group_clips):
+        key = (tuple(int(n) for n in lengths), int(group_clips))
+        cache = getattr(self, "_pipe_cache", None)
+        if cache is not None and cache["key"] == key:
+            return cache
+        groups = []
+        samp0 = row0 = 0
+        for g0 in range(0, len(lengths), group_clips):
+            lens = [int(n) for n in lengths[g0:g0 + group_clips]]
+            frames = [_ffi.num_frames(n, self.hop_size, self.end) for n in lens]
+            groups.append(dict(lens=lens, frames=frames, samp0=samp0, nsamp=sum(lens), row0=row0, rows=sum(frames)))
+            samp0 += sum(lens)
+            row0 += sum(frames)
+        max_s = max(g["nsamp"] for g in groups)
+        max_r = max(g["rows"] for g in groups)
+        sshape = (max_s,) if self.channels == 1 else (max_s, self.channels)
+        slots = [dict(sig=torch.empty(sshape, dtype=self.torch_dtype(), device=self.device),
+                      out=torch.empty((max_r, self.width), dtype=torch.float32, device=self.device)) for _ in range(2)]
+        for g in groups:  # per-group offsets live on the device for the whole pipeline lifetime
+            g["packed"] = [Packed(slots[s]["sig"][:g["nsamp"]], g["lens"], self.hop_size, self.end, g["frames"])
+                           for s in range(2)]
+        cache = dict(key=key, groups=groups, slots=slots, total_rows=row0, total_samples=samp0,
+                     h2d=torch.cuda.Stream(self.device), comp=torch.cuda.Stream(self.device),
+                     d2h=torch.cuda.Stream(self.device))
+        self._pipe_cache = cache
+        return cache
+
+    def process_batch_pinned(self, host_in: torch.Tensor, lengths: Sequence[int], host_out: torch.Tensor,
+                             group_clips: int = 4) -> torch.Tensor:
+        """Whole batch from a pinned packed host tensor to a pinned host result matrix.
+
+        Clips are processed in groups; the host->device copy of group g+1 and the device->host copy
+        of group g-1 overlap the kernels of group g on three streams with two device slots.  The
+        current stream is joined at the end (but not synchronised with the host).
+        """
+        pipe = self._pipeline(lengths, group_clips)
+        if host_in.shape[0] != pipe["total_samples"] or tuple(host_out.shape) != (pipe["total_rows"], self.width):
+            raise ValueError("host_in / host_out shapes do not match `lengths`")
+        cur = torch.cuda.current_stream(self.device)
+        start = torch.cuda.Event()
+        start.record(cur)
+        h2d, comp, d2h = pipe["h2d"], pipe["comp"], pipe["d2h"]
+        for s in (h2d, comp, d2h):
+            s.wait_event(start)
+        ev_comp = [None, None]   # last compute on each slot (input slot free for the next H2D)
+        ev_d2h = [None, None]    # last D2H on each slot (output slot free for the next compute)
+        for gi, g in enumerate(pipe["groups"]):
+            slot = gi & 1
+            buf = pipe["slots"][slot]
+            if ev_comp[slot] is not None:
+                h2d.wait_event(ev_comp[slot])
+            with torch.cuda.stream(h2d):
+                buf["sig"][:g["nsamp"]].copy_(host_in[g["samp0"]:g["samp0"] + g["nsamp"]], non_blocking=True)
+                ev_h2d = torch.cuda.Event()
+                ev_h2d.record(h2d)
+            comp.wait_event(ev_h2d)
+            if ev_d2h[slot] is not None:
+                comp.wait_event(ev_d2h[slot])
+            with torch.cuda.stream(comp):
+                self.run_packed(g["packed"][slot], buf["out"][:g["rows"]])
+                ev_comp[slot] = torch.cuda.Event()
+                ev_comp[slot].record(comp)
+            d2h.wait_event(ev_comp[slot])
+            with torch.cuda.stream(d2h):
+                host_out[g["row0"]:g["row0"] + g["rows"]].copy_(buf["out"][:g["rows"]], non_blocking=True)
+                ev_d2h[slot] = torch.cuda.Event()
+                ev_d2h[slot].record(d2h)
+        for ev in ev_d2h:
+            if ev is not None:
+                cur.wait_event(ev)
+        return host_out
 
     # ---- host in / host out ----------------------------------------------------------------
     def process_batch(self, signals: Sequence, return_tensors: bool = False):
