@@ -135,7 +135,7 @@ int build_res(b200spec_plan *pl, const b200spec_res_desc &d, ResPlan &r) {
   for (int q = 0; q <= 128; ++q)
     for (int n3 = 0; n3 < R3; ++n3) {
       double a = -2.0 * PI * (double)(n3 * q) / (double)N;
-      tw3[q * R3 + n3] = make_float2((float)cos(a), (float)sin(a));
+      tw3[n3 * 129 + q] = make_float2((float)cos(a), (float)sin(a));
     }
   for (int k3 = 0; k3 < R3; ++k3)
     for (int q = 0; q <= 128; ++q) {
@@ -164,21 +164,26 @@ int build_res(b200spec_plan *pl, const b200spec_res_desc &d, ResPlan &r) {
   }
   r.nnz = nnz;
   r.kmax = kmax;
+  // every band is cut into contiguous slices of (about) nnz/128 taps; an ODD slice length keeps the
+  // lanes that work on neighbouring slices of one band on distinct shared-memory banks
   int seg_max = (nnz + b2::kGroupThreads - 1) / b2::kGroupThreads;
-  if (seg_max < 8) seg_max = 8;
-  if (seg_max > 32) seg_max = 32;
+  if (seg_max < 9) seg_max = 9;
+  if (seg_max > 33) seg_max = 33;
+  seg_max |= 1;
   std::vector<b2::Seg> segs;
   std::vector<int> bseg(B + 1, 0);
   for (int j = 0; j < B; ++j) {
     bseg[j] = (int)segs.size();
     const int L = d.band_len[j];
     const int S = (L + seg_max - 1) / seg_max;
-    for (int i = 0; i < S; ++i) {
+    int chunk = S > 0 ? (L + S - 1) / S : 0;
+    if (S > 1) chunk |= 1;
+    for (int off = 0; off < L; off += chunk) {
       b2::Seg s;
-      s.k0 = d.band_start[j] + i;
-      s.w0 = d.band_woff[j] + i;
-      s.cnt = (L - i + S - 1) / S;
-      s.stride = S;
+      s.k0 = d.band_start[j] + off;
+      s.w0 = d.band_woff[j] + off;
+      s.cnt = (L - off < chunk) ? L - off : chunk;
+      s.pad = 0;
       segs.push_back(s);
     }
   }
@@ -217,7 +222,7 @@ int carve_workspace(void *ws, size_t bytes, int n_clips, Workspace &w) {
 }
 
 int choose_chunk(const b200spec_plan *pl, int F, long long total_frames, int kd) {
-  const int G = (F == 8192) ? 2 : 3;
+  const int G = (F == 8192) ? 2 : 4;
   const long long slots = (long long)pl->num_sms * G;
   long long chunk = total_frames / (slots * 8);
   const int lo = kd > 0 ? 16 : 4;

@@ -8,8 +8,8 @@
 // z[m] = x[2m] + i x[2m+1] (window folded into the load, pre-scaled by 1/2), followed by the
 // even/odd split  X[k] = E[k] + W_F^k O[k].  N = 16 * 16 * R3 with R3 = F/512 in {2,4,8,16}:
 //
-//   pass 1  thread b in [0,16*R3):  DFT16 over n1 of z[n1*16*R3 + b]            -> buf1[k1][b]
-//   pass 2  thread (k1,n3):         twiddle W_256^(n2*k1), DFT16 over n2       -> buf2[n3][k1+16*k2]
+//   pass 1  thread b in [0,16*R3):  DFT16 over n1 of z[n1*16*R3 + b]            -> buf[k1][b]
+//   pass 2  thread (k1,n3):         twiddle W_256^(n2*k1), DFT16 over n2, IN PLACE (k2 replaces n2)
 //   pass 3  unit u in [0,128):      butterflies q=u and q=256-u of radix R3 are combined BEFORE the
 //           DFT (P = a + conj(b), M = a - conj(b)), so E and O come out of two DFT_R3 directly and
 //           both bins k and N-k of the real spectrum are produced in registers.
@@ -47,9 +47,8 @@ struct FftCfg {
   static constexpr int FPG = (BPF >= kGroupThreads) ? 1 : kGroupThreads / BPF;  // frames per group step
   static constexpr int IT12 = (BPF >= kGroupThreads) ? BPF / kGroupThreads : 1; // pass-1/2 butterflies per thread
   static constexpr int S1 = BPF + 1;       // buf1 row stride (float2), +1 keeps pass-2 reads conflict free
-  static constexpr int BUF1 = 16 * S1;     // float2 elements per frame
-  static constexpr int BUF2 = N;           // float2 elements per frame
-  static constexpr int TW3 = 129 * R3;     // tw3[q*R3 + n3] = W_N^(n3*q), q in [0,128]
+  static constexpr int BUF = 16 * S1;      // float2 elements of the single in-place buffer of a frame
+  static constexpr int TW3 = 129 * R3;     // tw3[n3*129 + q] = W_N^(n3*q), q in [0,128]
   static constexpr int PT = 129 * R3;      // pt[k3*129 + q] = -i * W_F^(q + 256*k3)
 };
 
@@ -143,51 +142,59 @@ struct Dft<16> {
 };
 
 // ---- pass 1: windowed load + DFT16 over n1 -----------------------------------------------------
-// `load(m)` returns the windowed complex sample z[m], m in [0, N).
+// One in-place buffer per frame: buf[k1 * S1 + j], j in [0, BPF).  `load(n1)` returns the windowed
+// complex sample z[n1 * BPF + b]; `p` = buf + b.
 template <int F, class Load>
-B2_HD void fft_pass1(int b, Load load, float2 *buf1) {
+B2_HD void fft_pass1(Load load, float2 *p) {
   using C = FftCfg<F>;
   float2 v[16];
 #pragma unroll
-  for (int n1 = 0; n1 < 16; ++n1) v[n1] = load(n1 * C::BPF + b);
+  for (int n1 = 0; n1 < 16; ++n1) v[n1] = load(n1);
   dft16(v);
 #pragma unroll
-  for (int k1 = 0; k1 < 16; ++k1) buf1[k1 * C::S1 + b] = v[dft_pos<16>(k1)];
+  for (int k1 = 0; k1 < 16; ++k1) p[k1 * C::S1] = v[dft_pos<16>(k1)];
 }
 
-// ---- pass 2: twiddle W_256^(n2*k1), DFT16 over n2 ----------------------------------------------
-// t2 in [0, BPF): k1 = t2 % 16, n3 = t2 / 16.  tw2[n2] = W_256^(n2*k1) for this thread's k1.
+// ---- pass 2: twiddle W_256^(n2*k1), DFT16 over n2, in place ------------------------------------
+// thread (k1, n3): p = buf + k1 * S1 + n3; element n2 sits at p[n2 * R3]; output k2 replaces it.
 template <int F>
-B2_HD void fft_pass2(int t2, const float2 (&tw2)[16], const float2 *buf1, float2 *buf2) {
+B2_HD void fft_pass2(const float2 (&tw2)[16], float2 *p) {
   using C = FftCfg<F>;
-  const int k1 = t2 & 15, n3 = t2 >> 4;
   float2 v[16];
 #pragma unroll
-  for (int n2 = 0; n2 < 16; ++n2) v[n2] = buf1[k1 * C::S1 + n2 * C::R3 + n3];
+  for (int n2 = 0; n2 < 16; ++n2) v[n2] = p[n2 * C::R3];
 #pragma unroll
   for (int n2 = 1; n2 < 16; ++n2) v[n2] = cmul(v[n2], tw2[n2]);
   dft16(v);
 #pragma unroll
-  for (int k2 = 0; k2 < 16; ++k2) buf2[n3 * 256 + k1 + 16 * k2] = v[dft_pos<16>(k2)];
+  for (int k2 = 0; k2 < 16; ++k2) p[k2 * C::R3] = v[dft_pos<16>(k2)];
+}
+
+// column q = k1 + 16*k2 of the pass-2 output starts at this offset (elements n3 = 0..R3-1 follow)
+template <int F>
+B2_HD constexpr int fft_col_offset(int q) {
+  return (q & 15) * FftCfg<F>::S1 + (q >> 4) * FftCfg<F>::R3;
 }
 
 // ---- pass 3: last radix-R3 pass fused with the real-spectrum split -----------------------------
-// unit u in [1,127]: emits bins k = u + 256*k3 and N - k.   emit(k, X) receives each bin once.
+// unit u in [1,127]: pa / pb = columns u and 256-u; tw3u = tw3 + u (tw3[n3*129 + q] = W_N^(n3 q));
+// ptu = pt + u (pt[k3*129 + q] = -i W_F^(q + 256 k3)).  Emits bins k = u + 256*k3 and N - k.
 template <int F, class Emit>
-B2_HD void fft_pass3_unit(int u, const float2 *buf2, const float2 *tw3, const float2 *pt, Emit emit) {
+B2_HD void fft_pass3_unit(int u, const float2 *pa, const float2 *pb, const float2 *tw3u, const float2 *ptu,
+                          Emit emit) {
   using C = FftCfg<F>;
   constexpr int R3 = C::R3;
   float2 P[R3], M[R3];
 #pragma unroll
   for (int n3 = 0; n3 < R3; ++n3) {
-    float2 a = buf2[n3 * 256 + u];
-    float2 b = buf2[n3 * 256 + 256 - u];
+    float2 a = pa[n3];
+    float2 b = pb[n3];
     P[n3] = make_float2(a.x + b.x, a.y - b.y);  // a + conj(b)
     M[n3] = make_float2(a.x - b.x, a.y + b.y);  // a - conj(b)
   }
 #pragma unroll
   for (int n3 = 1; n3 < R3; ++n3) {
-    float2 w = tw3[u * R3 + n3];
+    float2 w = tw3u[n3 * 129];
     P[n3] = cmul(P[n3], w);
     M[n3] = cmul(M[n3], w);
   }
@@ -196,21 +203,22 @@ B2_HD void fft_pass3_unit(int u, const float2 *buf2, const float2 *tw3, const fl
 #pragma unroll
   for (int k3 = 0; k3 < R3; ++k3) {
     float2 E = P[dft_pos<R3>(k3)];
-    float2 T = cmul(M[dft_pos<R3>(k3)], pt[k3 * 129 + u]);
+    float2 T = cmul(M[dft_pos<R3>(k3)], ptu[k3 * 129]);
     const int k = u + 256 * k3;
     emit(k, cadd(E, T));
     emit(C::N - k, cconj(csub(E, T)));
   }
 }
 
-// unit 0: the two self-paired butterflies q = 0 (bins 256*k3) and q = 128 (bins 128 + 256*k3)
+// the two self-paired butterflies q = 0 (bins 256*k3) and q = 128 (bins 128 + 256*k3)
 template <int F, class Emit>
-B2_HD void fft_pass3_unit0(const float2 *buf2, const float2 *tw3, const float2 *pt, Emit emit) {
+B2_HD void fft_pass3_special(const float2 *buf, const float2 *tw3, const float2 *pt, Emit emit) {
   using C = FftCfg<F>;
   constexpr int R3 = C::R3;
   float2 Z[R3];
+  const float2 *p0 = buf + fft_col_offset<F>(0);
 #pragma unroll
-  for (int n3 = 0; n3 < R3; ++n3) Z[n3] = buf2[n3 * 256];
+  for (int n3 = 0; n3 < R3; ++n3) Z[n3] = p0[n3];
   Dft<R3>::run(Z);
 #pragma unroll
   for (int k3 = 0; k3 < R3; ++k3) {
@@ -218,10 +226,11 @@ B2_HD void fft_pass3_unit0(const float2 *buf2, const float2 *tw3, const float2 *
     float2 b = cconj(Z[dft_pos<R3>((R3 - k3) % R3)]);
     emit(256 * k3, cadd(cadd(a, b), cmul(csub(a, b), pt[k3 * 129])));
   }
+  const float2 *p1 = buf + fft_col_offset<F>(128);
 #pragma unroll
   for (int n3 = 0; n3 < R3; ++n3) {
-    float2 a = buf2[n3 * 256 + 128];
-    Z[n3] = n3 == 0 ? a : cmul(a, tw3[128 * R3 + n3]);
+    float2 a = p1[n3];
+    Z[n3] = n3 == 0 ? a : cmul(a, tw3[n3 * 129 + 128]);
   }
   Dft<R3>::run(Z);
 #pragma unroll

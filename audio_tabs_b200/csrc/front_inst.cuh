@@ -8,7 +8,7 @@ namespace b2 {
 // groups of 128 threads per CTA for each frame size (bounded by shared memory and registers)
 template <int F>
 struct GroupsPerCta {
-  static constexpr int value = (F == 8192) ? 2 : 3;
+  static constexpr int value = (F == 8192) ? 2 : 4;
 };
 
 struct LaunchResult {

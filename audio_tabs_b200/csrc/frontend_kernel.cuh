@@ -10,7 +10,8 @@
 // Execution model
 //   grid   = one CTA per SM (persistent), G groups of 128 threads per CTA
 //   group  = pulls tasks (clip, chunk of frames) from a global counter; processes FPG frames per
-//            step entirely in shared memory; named barriers (bar.sync id,128) keep groups independent
+//            step entirely in shared memory (one in-place FFT buffer per frame); named barriers
+//            (bar.sync id,128) keep the groups independent of each other
 //   tables = window / twiddles / banded filterbank are staged once per CTA in shared memory,
 //            pass-2 twiddles live in registers
 #pragma once
@@ -24,11 +25,11 @@ namespace b2 {
 enum InputKind { IN_F32_MONO = 0, IN_F32_STEREO = 1, IN_I16_MONO = 2, IN_I16_STEREO = 3 };
 enum KernelMode { MODE_LOGFILT = 0, MODE_SPECTRUM = 1 };
 
-struct Seg {      // one interleaved slice of a filterbank band
-  int k0;         // first FFT bin
-  int w0;         // first weight index
-  int cnt;        // number of taps
-  int stride;     // tap stride in bins (= number of slices of the band)
+struct Seg {   // one contiguous slice of a filterbank band (odd length keeps lanes on distinct banks)
+  int k0;      // first FFT bin
+  int w0;      // first weight index
+  int cnt;     // number of taps
+  int pad;
 };
 
 struct FrontParams {
@@ -44,9 +45,9 @@ struct FrontParams {
   int origin;
   // tables (plan-owned, device)
   const float *window;  // F, already * 1/2 (and / 32767 for int16)
-  const float2 *tw2;    // [16][16]
-  const float2 *tw3;    // [129][R3]
-  const float2 *pt;     // [R3][129]
+  const float2 *tw2;    // [16][16]   tw2[k1*16 + n2] = W_256^(n2 k1)
+  const float2 *tw3;    // [R3][129]  tw3[n3*129 + q] = W_N^(n3 q)
+  const float2 *pt;     // [R3][129]  pt[k3*129 + q]  = -i W_F^(q + 256 k3)
   // filterbank (MODE_LOGFILT)
   int num_bands, nnz, nseg, kmax;
   const float *fbw;
@@ -70,7 +71,8 @@ struct FrontParams {
   int spec_complex;
   // shared-memory carve-up (byte offsets), filled by front_smem_layout()
   int o_win, o_tw3, o_pt, o_fbw, o_segs, o_bseg, o_groups, group_bytes;
-  int g_buf2, g_partial, g_hist, g_lrow, g_red, g_task;  // offsets inside a group's block
+  int g_mags, g_partial, g_hist, g_lrow, g_red, g_task;  // offsets inside a group's block
+  int mag_stride;                                        // floats per frame in the magnitude buffer
 };
 
 template <int F>
@@ -89,10 +91,11 @@ inline size_t front_smem_layout(FrontParams &p, int mode, int G) {
   }
   p.o_groups = (int)o;
   size_t g = 0;
-  g = al(g + sizeof(float2) * C::FPG * C::BUF1);  // buf1 (magnitudes alias it after pass 2)
-  p.g_buf2 = (int)g;    g = al(g + sizeof(float2) * C::FPG * C::BUF2);
-  p.g_partial = p.g_hist = p.g_lrow = (int)g;
+  g = al(g + sizeof(float2) * C::FPG * C::BUF);  // in-place FFT buffers
+  p.g_mags = p.g_partial = p.g_hist = p.g_lrow = (int)g;
+  p.mag_stride = C::N + 4;
   if (mode == MODE_LOGFILT) {
+    p.g_mags = (int)g;    g = al(g + sizeof(float) * C::FPG * p.mag_stride);
     p.g_partial = (int)g; g = al(g + sizeof(float) * C::FPG * p.nseg);
     p.g_hist = (int)g;    g = al(g + sizeof(float) * (p.diff_frames > 0 ? p.diff_frames : 1) * p.num_bands);
     p.g_lrow = (int)g;    g = al(g + sizeof(float) * C::FPG * p.num_bands);
@@ -111,9 +114,11 @@ __device__ __forceinline__ void group_bar(int g) {
 
 __device__ __forceinline__ float fast_sqrt(float v) {
   float r;
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v));  // max rel. error 2^-23
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));  // one MUFU; max rel. error 2^-23
   return r;
 }
+
+__device__ __forceinline__ float cabs_fast(float2 X) { return fast_sqrt(fmaf(X.x, X.x, X.y * X.y)); }
 
 // ---- sample access: madmom Signal dtype + remix (audio/signal.py) ------------------------------
 template <int IN>
@@ -146,7 +151,7 @@ __device__ __forceinline__ const void *clip_base(const void *sig, long long off)
 template <int F, int IN, int MODE, int G>
 __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams p) {
   using C = FftCfg<F>;
-  constexpr int FPG = C::FPG, N = C::N;
+  constexpr int FPG = C::FPG, N = C::N, R3 = C::R3, S1 = C::S1;
   extern __shared__ __align__(16) unsigned char smem[];
   float *s_win = reinterpret_cast<float *>(smem + p.o_win);
   float2 *s_tw3 = reinterpret_cast<float2 *>(smem + p.o_tw3);
@@ -167,21 +172,29 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
 
   const int g = threadIdx.x / kGroupThreads, tid = threadIdx.x % kGroupThreads;
   unsigned char *gmem = smem + p.o_groups + (size_t)g * p.group_bytes;
-  float2 *buf1 = reinterpret_cast<float2 *>(gmem);
-  float2 *buf2 = reinterpret_cast<float2 *>(gmem + p.g_buf2);
+  float2 *buf = reinterpret_cast<float2 *>(gmem);
+  float *s_mags = reinterpret_cast<float *>(gmem + p.g_mags);
   float *s_partial = reinterpret_cast<float *>(gmem + p.g_partial);
   float *s_hist = reinterpret_cast<float *>(gmem + p.g_hist);
   float *s_lrow = reinterpret_cast<float *>(gmem + p.g_lrow);
   float *s_red = reinterpret_cast<float *>(gmem + p.g_red);
   volatile int *s_task = reinterpret_cast<volatile int *>(gmem + p.g_task);
 
-  // pass-2 twiddles of this thread's k1 stay in registers for the whole kernel
-  float2 tw2r[16];
+  // per-thread constants ---------------------------------------------------------------------
+  float2 tw2r[16];                       // pass-2 twiddles of this thread's k1
 #pragma unroll
   for (int n2 = 0; n2 < 16; ++n2) tw2r[n2] = __ldg(&p.tw2[(tid & 15) * 16 + n2]);
+  const int fl12 = (FPG > 1) ? tid / C::BPF : 0;            // frame slot this thread serves in pass 1/2
+  const int b12 = (FPG > 1) ? tid % C::BPF : tid;           // butterfly index in pass 1/2 (first iteration)
+  float2 *p1 = buf + fl12 * C::BUF + b12;                               // pass-1 store base
+  const float *w1 = s_win + 2 * b12;                                    // window pairs of this butterfly
+  float2 *p2 = buf + fl12 * C::BUF + (b12 & 15) * S1 + (b12 >> 4);      // pass-2 in-place base (k1, n3)
+  const int u = tid;                                                    // pass-3 unit
+  const int pa_off = fft_col_offset<F>(u), pb_off = fft_col_offset<F>((256 - u) & 255);
+  const int mstride = p.mag_stride;
 
   const int total_tasks = p.task_off[p.n_clips];
-  const int B = p.num_bands, kd = p.diff_frames;
+  const int B = p.num_bands, kd = p.diff_frames, nseg = p.nseg;
 
   for (;;) {
     if (tid == 0) *s_task = atomicAdd(p.task_counter, 1);
@@ -208,44 +221,34 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
 
     for (int f = fs; f < f1; f += FPG) {
       // ---------------- pass 1: frame load * window, DFT16 ----------------
-      {
-        const int fl = (FPG > 1) ? tid / C::BPF : 0;
-        const int frame = f + fl;
-        if (frame < f1) {
-          const long long s0 = (long long)((double)frame * p.hop) - (F / 2) - p.origin;
-          float2 *b1 = buf1 + fl * C::BUF1;
-          const bool interior = (s0 >= 0) && (s0 + F <= nsamp);
+      if (f + fl12 < f1) {
+        const long long s0 = (long long)((double)(f + fl12) * p.hop) - (F / 2) - p.origin;
+        const bool interior = (s0 >= 0) && (s0 + F <= nsamp);
 #pragma unroll 1
-          for (int it = 0; it < C::IT12; ++it) {
-            const int b = (FPG > 1) ? tid % C::BPF : tid + it * kGroupThreads;
-            if (interior) {
-              fft_pass1<F>(b, [&](int m) {
-                float2 w = *reinterpret_cast<const float2 *>(&s_win[2 * m]);
-                return make_float2(w.x * S.at(s0 + 2 * m), w.y * S.at(s0 + 2 * m + 1));
-              }, b1);
-            } else {
-              fft_pass1<F>(b, [&](int m) {
-                float2 w = *reinterpret_cast<const float2 *>(&s_win[2 * m]);
-                const long long sa = s0 + 2 * m, sb = sa + 1;
-                float xa = (sa >= 0 && sa < nsamp) ? S.at(sa) : 0.f;
-                float xb = (sb >= 0 && sb < nsamp) ? S.at(sb) : 0.f;
-                return make_float2(w.x * xa, w.y * xb);
-              }, b1);
-            }
+        for (int it = 0; it < C::IT12; ++it) {
+          const long long sb = s0 + 2 * (b12 + it * kGroupThreads);
+          const float *wp = w1 + 2 * it * kGroupThreads;
+          if (interior) {
+            fft_pass1<F>([&](int n1) {
+              float2 w = *reinterpret_cast<const float2 *>(wp + 2 * n1 * C::BPF);
+              return make_float2(w.x * S.at(sb + 2 * n1 * C::BPF), w.y * S.at(sb + 2 * n1 * C::BPF + 1));
+            }, p1 + it * kGroupThreads);
+          } else {
+            fft_pass1<F>([&](int n1) {
+              float2 w = *reinterpret_cast<const float2 *>(wp + 2 * n1 * C::BPF);
+              const long long sa = sb + 2 * n1 * C::BPF, sc = sa + 1;
+              float xa = (sa >= 0 && sa < nsamp) ? S.at(sa) : 0.f;
+              float xb = (sc >= 0 && sc < nsamp) ? S.at(sc) : 0.f;
+              return make_float2(w.x * xa, w.y * xb);
+            }, p1 + it * kGroupThreads);
           }
         }
       }
       group_bar(g);
-      // ---------------- pass 2: twiddle, DFT16 ----------------
-      {
-        const int fl = (FPG > 1) ? tid / C::BPF : 0;
-        if (f + fl < f1) {
+      // ---------------- pass 2: twiddle, DFT16, in place ----------------
+      if (f + fl12 < f1) {
 #pragma unroll 1
-          for (int it = 0; it < C::IT12; ++it) {
-            const int t2 = (FPG > 1) ? tid % C::BPF : tid + it * kGroupThreads;
-            fft_pass2<F>(t2, tw2r, buf1 + fl * C::BUF1, buf2 + fl * C::BUF2);
-          }
-        }
+        for (int it = 0; it < C::IT12; ++it) fft_pass2<F>(tw2r, p2 + it * (kGroupThreads >> 4));
       }
       group_bar(g);
       // ---------------- pass 3: last radix + real split (+ magnitude) ----------------
@@ -253,52 +256,58 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
       for (int fl = 0; fl < FPG; ++fl) {
         const int frame = f + fl;
         if (frame >= f1) break;
-        const float2 *b2p = buf2 + fl * C::BUF2;
+        const float2 *fb = buf + fl * C::BUF;
         if (MODE == MODE_LOGFILT) {
-          float *mags = reinterpret_cast<float *>(buf1 + fl * C::BUF1);
-          const int kmax = p.kmax;
-          auto emit = [&](int k, float2 X) {
-            if (k < kmax) mags[k] = fast_sqrt(fmaf(X.x, X.x, X.y * X.y));
-          };
-          if (tid == 0) fft_pass3_unit0<F>(b2p, s_tw3, s_pt, emit);
-          else fft_pass3_unit<F>(tid, b2p, s_tw3, s_pt, emit);
+          float *mags = s_mags + fl * mstride;
+          auto emit = [&](int k, float2 X) { mags[k] = cabs_fast(X); };
+          if (tid == 0) fft_pass3_special<F>(fb, s_tw3, s_pt, emit);
+          else fft_pass3_unit<F>(u, fb + pa_off, fb + pb_off, s_tw3 + u, s_pt + u, emit);
         } else {
           if (frame >= f0) {
             const long long row = row0 + frame;
             if (p.spec_complex) {
               float2 *o = reinterpret_cast<float2 *>(p.spec_out) + row * N;
               auto emit = [&](int k, float2 X) { o[k] = X; };
-              if (tid == 0) fft_pass3_unit0<F>(b2p, s_tw3, s_pt, emit);
-              else fft_pass3_unit<F>(tid, b2p, s_tw3, s_pt, emit);
+              if (tid == 0) fft_pass3_special<F>(fb, s_tw3, s_pt, emit);
+              else fft_pass3_unit<F>(u, fb + pa_off, fb + pb_off, s_tw3 + u, s_pt + u, emit);
             } else {
               float *o = p.spec_out + row * N;
-              auto emit = [&](int k, float2 X) { o[k] = fast_sqrt(fmaf(X.x, X.x, X.y * X.y)); };
-              if (tid == 0) fft_pass3_unit0<F>(b2p, s_tw3, s_pt, emit);
-              else fft_pass3_unit<F>(tid, b2p, s_tw3, s_pt, emit);
+              auto emit = [&](int k, float2 X) { o[k] = cabs_fast(X); };
+              if (tid == 0) fft_pass3_special<F>(fb, s_tw3, s_pt, emit);
+              else fft_pass3_unit<F>(u, fb + pa_off, fb + pb_off, s_tw3 + u, s_pt + u, emit);
             }
           }
         }
       }
-      if (MODE != MODE_LOGFILT) continue;  // next pass-1 write to buf1 is ordered by the two barriers above
-      group_bar(g);
-      // ---------------- K2a: banded filterbank, interleaved slices -> partial sums ----------------
-      {
-        const int nseg = p.nseg;
-        for (int s = tid; s < nseg; s += kGroupThreads) {
-          const Seg sg = s_segs[s];
-          float acc[FPG];
+      group_bar(g);                          // all pass-3 reads done before the next pass 1 overwrites buf
+      if (MODE != MODE_LOGFILT) continue;
+      // ---------------- K2a: banded filterbank, contiguous slices -> partial sums ----------------
+      for (int s = tid; s < nseg; s += kGroupThreads) {
+        const Seg sg = s_segs[s];
+        const float *wp = s_fbw + sg.w0;
+        const float *mp = s_mags + sg.k0;
+        float acc[FPG][2];
 #pragma unroll
-          for (int fl = 0; fl < FPG; ++fl) acc[fl] = 0.f;
-          int k = sg.k0, wi = sg.w0;
-          for (int i = 0; i < sg.cnt; ++i, k += sg.stride, wi += sg.stride) {
-            const float w = s_fbw[wi];
+        for (int fl = 0; fl < FPG; ++fl) acc[fl][0] = acc[fl][1] = 0.f;
+        int i = 0;
+        for (; i + 4 <= sg.cnt; i += 4) {
+          const float w0 = wp[i], w1 = wp[i + 1], w2 = wp[i + 2], w3 = wp[i + 3];
 #pragma unroll
-            for (int fl = 0; fl < FPG; ++fl)
-              acc[fl] = fmaf(w, reinterpret_cast<const float *>(buf1 + fl * C::BUF1)[k], acc[fl]);
+          for (int fl = 0; fl < FPG; ++fl) {
+            const float *m = mp + fl * mstride + i;
+            acc[fl][0] = fmaf(w0, m[0], acc[fl][0]);
+            acc[fl][1] = fmaf(w1, m[1], acc[fl][1]);
+            acc[fl][0] = fmaf(w2, m[2], acc[fl][0]);
+            acc[fl][1] = fmaf(w3, m[3], acc[fl][1]);
           }
-#pragma unroll
-          for (int fl = 0; fl < FPG; ++fl) s_partial[fl * nseg + s] = acc[fl];
         }
+        for (; i < sg.cnt; ++i) {
+          const float w0 = wp[i];
+#pragma unroll
+          for (int fl = 0; fl < FPG; ++fl) acc[fl][0] = fmaf(w0, mp[fl * mstride + i], acc[fl][0]);
+        }
+#pragma unroll
+        for (int fl = 0; fl < FPG; ++fl) s_partial[fl * nseg + s] = acc[fl][0] + acc[fl][1];
       }
       group_bar(g);
       // ---------------- K2b/K3: band sum, log10, lagged difference, stacked store ----------------
@@ -312,7 +321,7 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
           const int frame = f + fl;
           if (frame < f1) {
             float y = 0.f;
-            for (int s = sb; s < se; ++s) y += s_partial[fl * p.nseg + s];
+            for (int s = sb; s < se; ++s) y += s_partial[fl * nseg + s];
             float L = p.log_enabled ? log10f(__fadd_rn(__fmul_rn(p.mul, y), p.add)) : y;
             float D = 0.f;
             if (kd > 0) {

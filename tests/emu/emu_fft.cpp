@@ -1,6 +1,7 @@
 // CPU emulation of the thread-mapped FFT passes in audio_tabs_b200/csrc/fft_core.cuh.
-// Test infrastructure only: runs every "thread" of every pass sequentially and compares the
-// resulting half spectrum with a naive float64 DFT of the windowed frame.
+// Test infrastructure only: runs every "thread" of every pass sequentially (exactly the index
+// mapping k_front uses, including the in-place pass 2) and compares the resulting half spectrum
+// with a naive float64 DFT of the windowed frame.
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
@@ -27,27 +28,32 @@ double run_one(unsigned seed) {
   for (int q = 0; q <= 128; ++q)
     for (int n3 = 0; n3 < C::R3; ++n3) {
       double a = -2 * PI * ((double)n3 * q) / C::N;
-      tw3[q * C::R3 + n3] = make_float2((float)cos(a), (float)sin(a));
+      tw3[n3 * 129 + q] = make_float2((float)cos(a), (float)sin(a));
     }
   for (int k3 = 0; k3 < C::R3; ++k3)
     for (int q = 0; q <= 128; ++q) {
       double a = -2 * PI * (q + 256.0 * k3) / F;
-      // -i * W = -i (cos a + i sin a) = sin a - i cos a
-      pt[k3 * 129 + q] = make_float2((float)sin(a), (float)-cos(a));
+      pt[k3 * 129 + q] = make_float2((float)sin(a), (float)-cos(a));  // -i * exp(i a)
     }
-  std::vector<float2> buf1(C::BUF1), buf2(C::BUF2), X(C::N);
+  std::vector<float2> buf(C::BUF), X(C::N);
   std::vector<int> hits(C::N, 0);
-  auto load = [&](int m) { return make_float2(w[2 * m] * x[2 * m], w[2 * m + 1] * x[2 * m + 1]); };
-  for (int b = 0; b < C::BPF; ++b) b2::fft_pass1<F>(b, load, buf1.data());
+  for (int b = 0; b < C::BPF; ++b) {
+    auto load = [&](int n1) {
+      int m = n1 * C::BPF + b;
+      return make_float2(w[2 * m] * x[2 * m], w[2 * m + 1] * x[2 * m + 1]);
+    };
+    b2::fft_pass1<F>(load, buf.data() + b);
+  }
   for (int t2 = 0; t2 < C::BPF; ++t2) {
     float2 t[16];
     for (int n2 = 0; n2 < 16; ++n2) t[n2] = tw2[(t2 & 15) * 16 + n2];
-    b2::fft_pass2<F>(t2, t, buf1.data(), buf2.data());
+    b2::fft_pass2<F>(t, buf.data() + (t2 & 15) * C::S1 + (t2 >> 4));
   }
   auto emit = [&](int k, float2 v) { X[k] = v; hits[k]++; };
-  b2::fft_pass3_unit0<F>(buf2.data(), tw3.data(), pt.data(), emit);
-  for (int u = 1; u < 128; ++u) b2::fft_pass3_unit<F>(u, buf2.data(), tw3.data(), pt.data(), emit);
-  // reference
+  b2::fft_pass3_special<F>(buf.data(), tw3.data(), pt.data(), emit);
+  for (int u = 1; u < 128; ++u)
+    b2::fft_pass3_unit<F>(u, buf.data() + b2::fft_col_offset<F>(u), buf.data() + b2::fft_col_offset<F>(256 - u),
+                          tw3.data() + u, pt.data() + u, emit);
   double maxerr = 0, peak = 0;
   for (int k = 0; k < C::N; ++k) {
     if (hits[k] != 1) { printf("F=%d bin %d emitted %d times\n", F, k, hits[k]); return 1e9; }
