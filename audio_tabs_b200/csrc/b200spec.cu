@@ -2,6 +2,7 @@
 // No compute happens on the host; every entry point either fails loudly or launches sm_100a kernels.
 #include "../../include/b200spec.h"
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -56,14 +57,15 @@ struct ResPlan {
   int frame_size = 0;
   double hop = 0;
   int origin = 0;
-  int num_bands = 0, nnz = 0, nseg = 0, kmax = 0;
+  int num_bands = 0, nnz = 0, nseg = 0, nseg_pad = 0, kmax = 0;
   int log_enabled = 0;
   float mul = 1.f, add = 1.f;
   int diff_frames = 0, positive = 0;
   int num_classes = 0;
   // device tables
   float *d_window = nullptr;
-  float2 *d_tw2 = nullptr, *d_tw3 = nullptr, *d_pt = nullptr;
+  float2 *d_tw2 = nullptr, *d_tw3 = nullptr, *d_pt = nullptr, *d_wr = nullptr;
+  int *d_seg_order = nullptr;
   float *d_fbw = nullptr;
   b2::Seg *d_segs = nullptr;
   int *d_bseg = nullptr;
@@ -142,7 +144,13 @@ int build_res(b200spec_plan *pl, const b200spec_res_desc &d, ResPlan &r) {
       double a = -2.0 * PI * (double)(q + 256 * k3) / (double)F;
       pt[k3 * 129 + q] = make_float2((float)sin(a), (float)-cos(a));  // -i * exp(i a)
     }
+  std::vector<float2> wr(2 * R3);
+  for (int e = 0; e < 2 * R3; ++e) {
+    double a = -2.0 * PI * (double)e / (double)(2 * R3);
+    wr[e] = make_float2((float)cos(a), (float)sin(a));
+  }
   int rc;
+  if ((rc = upload(pl, wr.data(), wr.size(), &r.d_wr))) return rc;
   if ((rc = upload(pl, win.data(), win.size(), &r.d_window))) return rc;
   if ((rc = upload(pl, tw2.data(), tw2.size(), &r.d_tw2))) return rc;
   if ((rc = upload(pl, tw3.data(), tw3.size(), &r.d_tw3))) return rc;
@@ -189,6 +197,13 @@ int build_res(b200spec_plan *pl, const b200spec_res_desc &d, ResPlan &r) {
   }
   bseg[B] = (int)segs.size();
   r.nseg = (int)segs.size();
+  // processing order: longest slices first (stable), so every warp-round works on equal lengths
+  std::vector<int> order(segs.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return segs[a].cnt > segs[b].cnt; });
+  while (order.size() % b2::kGroupThreads) order.push_back(-1);
+  r.nseg_pad = (int)order.size();
+  if ((rc = upload(pl, order.data(), order.size(), &r.d_seg_order))) return rc;
   if ((rc = upload(pl, d.weights, (size_t)nnz, &r.d_fbw))) return rc;
   if ((rc = upload(pl, segs.data(), segs.size(), &r.d_segs))) return rc;
   if ((rc = upload(pl, bseg.data(), bseg.size(), &r.d_bseg))) return rc;
@@ -266,6 +281,9 @@ int launch_front(const b200spec_plan *pl, int res, int mode, const void *d_sig, 
   p.tw2 = r.d_tw2;
   p.tw3 = r.d_tw3;
   p.pt = r.d_pt;
+  p.wr = r.d_wr;
+  p.seg_order = r.d_seg_order;
+  p.nseg_pad = r.nseg_pad;
   p.num_bands = r.num_bands;
   p.nnz = r.nnz;
   p.nseg = r.nseg;

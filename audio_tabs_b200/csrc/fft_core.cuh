@@ -50,6 +50,8 @@ struct FftCfg {
   static constexpr int BUF = 16 * S1;      // float2 elements of the single in-place buffer of a frame
   static constexpr int TW3 = 129 * R3;     // tw3[n3*129 + q] = W_N^(n3*q), q in [0,128]
   static constexpr int PT = 129 * R3;      // pt[k3*129 + q] = -i * W_F^(q + 256*k3)
+  static constexpr int WR = 2 * R3;        // wr[e] = W_(2 R3)^e, used by the self-paired columns
+  static constexpr int TB = 4096 / N;      // frames per tail batch (filterbank/log/diff stage)
 };
 
 // ---- complex helpers ---------------------------------------------------------------------------
@@ -239,6 +241,35 @@ B2_HD void fft_pass3_special(const float2 *buf, const float2 *tw3, const float2 
     float2 b = cconj(Z[dft_pos<R3>(R3 - 1 - k3)]);
     emit(128 + 256 * k3, cadd(cadd(a, b), cmul(csub(a, b), pt[k3 * 129 + 128])));
   }
+}
+
+// Lane-parallel form of the two self-paired columns (what k_front runs: 2*R3 lanes of one warp,
+// one output bin per lane, no second code path for a whole thread):
+//   h = lane / R3 (0: q = 0, 1: q = 128), k3 = lane % R3, bin k = 128 h + 256 k3
+//   X[k] = E + pt[k] D,  E = 2 sum_n w_n Re(c_n),  D = 2 i sum_n w_n Im(c_n),
+//   w_n = W_(2 R3)^(n (2 k3 + h)) = wr[(n (2 k3 + h)) mod 2 R3],  c_n = element n of column q.
+template <int F>
+B2_HD float2 fft_pass3_selfpaired(int lane, const float2 *buf, const float2 *wr, const float2 *pt, int &bin) {
+  using C = FftCfg<F>;
+  constexpr int R3 = C::R3;
+  const int h = lane / R3, k3 = lane % R3;
+  const float2 *c = buf + (h ? fft_col_offset<F>(128) : fft_col_offset<F>(0));
+  const int step = 2 * k3 + h;
+  int e = 0;
+  float2 E = make_float2(0.f, 0.f), D = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int n = 0; n < R3; ++n) {
+    const float2 w = wr[e];
+    const float2 cn = c[n];
+    E.x = fmaf(w.x, cn.x, E.x);
+    E.y = fmaf(w.y, cn.x, E.y);
+    D.x = fmaf(w.x, cn.y, D.x);
+    D.y = fmaf(w.y, cn.y, D.y);
+    e = (e + step) & (2 * R3 - 1);
+  }
+  const float2 T = cmul(make_float2(-2.f * D.y, 2.f * D.x), pt[k3 * 129 + 128 * h]);
+  bin = 128 * h + 256 * k3;
+  return make_float2(fmaf(2.f, E.x, T.x), fmaf(2.f, E.y, T.y));
 }
 
 }  // namespace b2

@@ -48,11 +48,14 @@ struct FrontParams {
   const float2 *tw2;    // [16][16]   tw2[k1*16 + n2] = W_256^(n2 k1)
   const float2 *tw3;    // [R3][129]  tw3[n3*129 + q] = W_N^(n3 q)
   const float2 *pt;     // [R3][129]  pt[k3*129 + q]  = -i W_F^(q + 256 k3)
+  const float2 *wr;     // [2 R3]     wr[e] = W_(2 R3)^e
   // filterbank (MODE_LOGFILT)
   int num_bands, nnz, nseg, kmax;
   const float *fbw;
   const Seg *segs;
   const int *bseg;      // num_bands + 1
+  const int *seg_order; // nseg_pad: slices sorted by length (balanced warps), -1 = padding
+  int nseg_pad;
   int log_enabled;
   float mul, add;
   int diff_frames, positive;
@@ -70,7 +73,7 @@ struct FrontParams {
   float *spec_out;      // (rows, N) float or float2
   int spec_complex;
   // shared-memory carve-up (byte offsets), filled by front_smem_layout()
-  int o_win, o_tw3, o_pt, o_fbw, o_segs, o_bseg, o_groups, group_bytes;
+  int o_win, o_tw3, o_pt, o_wr, o_fbw, o_segs, o_bseg, o_order, o_groups, group_bytes;
   int g_mags, g_partial, g_hist, g_lrow, g_red, g_task;  // offsets inside a group's block
   int mag_stride;                                        // floats per frame in the magnitude buffer
 };
@@ -83,11 +86,13 @@ inline size_t front_smem_layout(FrontParams &p, int mode, int G) {
   p.o_win = (int)o; o = al(o + sizeof(float) * F);
   p.o_tw3 = (int)o; o = al(o + sizeof(float2) * C::TW3);
   p.o_pt = (int)o;  o = al(o + sizeof(float2) * C::PT);
-  p.o_fbw = p.o_segs = p.o_bseg = (int)o;
+  p.o_wr = (int)o;  o = al(o + sizeof(float2) * C::WR);
+  p.o_fbw = p.o_segs = p.o_bseg = p.o_order = (int)o;
   if (mode == MODE_LOGFILT) {
     p.o_fbw = (int)o;  o = al(o + sizeof(float) * p.nnz);
     p.o_segs = (int)o; o = al(o + sizeof(Seg) * p.nseg);
     p.o_bseg = (int)o; o = al(o + sizeof(int) * (p.num_bands + 1));
+    p.o_order = (int)o; o = al(o + sizeof(int) * p.nseg_pad);
   }
   p.o_groups = (int)o;
   size_t g = 0;
@@ -95,12 +100,12 @@ inline size_t front_smem_layout(FrontParams &p, int mode, int G) {
   p.g_mags = p.g_partial = p.g_hist = p.g_lrow = (int)g;
   p.mag_stride = C::N + 4;
   if (mode == MODE_LOGFILT) {
-    p.g_mags = (int)g;    g = al(g + sizeof(float) * C::FPG * p.mag_stride);
-    p.g_partial = (int)g; g = al(g + sizeof(float) * C::FPG * p.nseg);
+    p.g_mags = (int)g;    g = al(g + sizeof(float) * C::TB * p.mag_stride);
+    p.g_partial = (int)g; g = al(g + sizeof(float) * C::TB * p.nseg);
     p.g_hist = (int)g;    g = al(g + sizeof(float) * (p.diff_frames > 0 ? p.diff_frames : 1) * p.num_bands);
-    p.g_lrow = (int)g;    g = al(g + sizeof(float) * C::FPG * p.num_bands);
+    p.g_lrow = (int)g;    g = al(g + sizeof(float) * C::TB * p.num_bands);
   }
-  p.g_red = (int)g;  g = al(g + sizeof(float) * 4 * C::FPG);
+  p.g_red = (int)g;  g = al(g + sizeof(float) * 4 * C::TB);
   p.g_task = (int)g; g = al(g + 16);
   p.group_bytes = (int)g;
   return o + g * G;
@@ -151,22 +156,26 @@ __device__ __forceinline__ const void *clip_base(const void *sig, long long off)
 template <int F, int IN, int MODE, int G>
 __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams p) {
   using C = FftCfg<F>;
-  constexpr int FPG = C::FPG, N = C::N, R3 = C::R3, S1 = C::S1;
+  constexpr int FPG = C::FPG, N = C::N, R3 = C::R3, S1 = C::S1, TB = C::TB;
   extern __shared__ __align__(16) unsigned char smem[];
   float *s_win = reinterpret_cast<float *>(smem + p.o_win);
   float2 *s_tw3 = reinterpret_cast<float2 *>(smem + p.o_tw3);
   float2 *s_pt = reinterpret_cast<float2 *>(smem + p.o_pt);
+  float2 *s_wr = reinterpret_cast<float2 *>(smem + p.o_wr);
   float *s_fbw = reinterpret_cast<float *>(smem + p.o_fbw);
   Seg *s_segs = reinterpret_cast<Seg *>(smem + p.o_segs);
   int *s_bseg = reinterpret_cast<int *>(smem + p.o_bseg);
+  int *s_order = reinterpret_cast<int *>(smem + p.o_order);
 
   for (int i = threadIdx.x; i < F; i += blockDim.x) s_win[i] = p.window[i];
   for (int i = threadIdx.x; i < C::TW3; i += blockDim.x) s_tw3[i] = p.tw3[i];
   for (int i = threadIdx.x; i < C::PT; i += blockDim.x) s_pt[i] = p.pt[i];
+  for (int i = threadIdx.x; i < C::WR; i += blockDim.x) s_wr[i] = p.wr[i];
   if (MODE == MODE_LOGFILT) {
     for (int i = threadIdx.x; i < p.nnz; i += blockDim.x) s_fbw[i] = p.fbw[i];
     for (int i = threadIdx.x; i < p.nseg; i += blockDim.x) s_segs[i] = p.segs[i];
     for (int i = threadIdx.x; i <= p.num_bands; i += blockDim.x) s_bseg[i] = p.bseg[i];
+    for (int i = threadIdx.x; i < p.nseg_pad; i += blockDim.x) s_order[i] = p.seg_order[i];
   }
   __syncthreads();
 
@@ -219,151 +228,165 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
     const int fs = (MODE == MODE_LOGFILT && kd > 0) ? max(0, f0 - kd) : f0;  // warm-up rows for the diff
     Samples<IN> S{clip_base<IN>(p.sig, samp0)};
 
-    for (int f = fs; f < f1; f += FPG) {
-      // ---------------- pass 1: frame load * window, DFT16 ----------------
-      if (f + fl12 < f1) {
-        const long long s0 = (long long)((double)(f + fl12) * p.hop) - (F / 2) - p.origin;
-        const bool interior = (s0 >= 0) && (s0 + F <= nsamp);
+    for (int fb = fs; fb < f1; fb += TB) {
+      // =============== FFT of the TB frames of this tail batch, FPG frames per step ===============
 #pragma unroll 1
-        for (int it = 0; it < C::IT12; ++it) {
-          const long long sb = s0 + 2 * (b12 + it * kGroupThreads);
-          const float *wp = w1 + 2 * it * kGroupThreads;
-          if (interior) {
-            fft_pass1<F>([&](int n1) {
-              float2 w = *reinterpret_cast<const float2 *>(wp + 2 * n1 * C::BPF);
-              return make_float2(w.x * S.at(sb + 2 * n1 * C::BPF), w.y * S.at(sb + 2 * n1 * C::BPF + 1));
-            }, p1 + it * kGroupThreads);
-          } else {
-            fft_pass1<F>([&](int n1) {
-              float2 w = *reinterpret_cast<const float2 *>(wp + 2 * n1 * C::BPF);
-              const long long sa = sb + 2 * n1 * C::BPF, sc = sa + 1;
-              float xa = (sa >= 0 && sa < nsamp) ? S.at(sa) : 0.f;
-              float xb = (sc >= 0 && sc < nsamp) ? S.at(sc) : 0.f;
-              return make_float2(w.x * xa, w.y * xb);
-            }, p1 + it * kGroupThreads);
-          }
-        }
-      }
-      group_bar(g);
-      // ---------------- pass 2: twiddle, DFT16, in place ----------------
-      if (f + fl12 < f1) {
+      for (int sub = 0; sub < TB; sub += FPG) {
+        const int f = fb + sub;
+        if (f >= f1) break;
+        // ---------------- pass 1: frame load * window, DFT16 ----------------
+        if (f + fl12 < f1) {
+          const long long s0 = (long long)((double)(f + fl12) * p.hop) - (F / 2) - p.origin;
+          const bool interior = (s0 >= 0) && (s0 + F <= nsamp);
 #pragma unroll 1
-        for (int it = 0; it < C::IT12; ++it) fft_pass2<F>(tw2r, p2 + it * (kGroupThreads >> 4));
-      }
-      group_bar(g);
-      // ---------------- pass 3: last radix + real split (+ magnitude) ----------------
-#pragma unroll 1
-      for (int fl = 0; fl < FPG; ++fl) {
-        const int frame = f + fl;
-        if (frame >= f1) break;
-        const float2 *fb = buf + fl * C::BUF;
-        if (MODE == MODE_LOGFILT) {
-          float *mags = s_mags + fl * mstride;
-          auto emit = [&](int k, float2 X) { mags[k] = cabs_fast(X); };
-          if (tid == 0) fft_pass3_special<F>(fb, s_tw3, s_pt, emit);
-          else fft_pass3_unit<F>(u, fb + pa_off, fb + pb_off, s_tw3 + u, s_pt + u, emit);
-        } else {
-          if (frame >= f0) {
-            const long long row = row0 + frame;
-            if (p.spec_complex) {
-              float2 *o = reinterpret_cast<float2 *>(p.spec_out) + row * N;
-              auto emit = [&](int k, float2 X) { o[k] = X; };
-              if (tid == 0) fft_pass3_special<F>(fb, s_tw3, s_pt, emit);
-              else fft_pass3_unit<F>(u, fb + pa_off, fb + pb_off, s_tw3 + u, s_pt + u, emit);
+          for (int it = 0; it < C::IT12; ++it) {
+            const long long sb = s0 + 2 * (b12 + it * kGroupThreads);
+            const float *wp = w1 + 2 * it * kGroupThreads;
+            if (interior) {
+              fft_pass1<F>([&](int n1) {
+                float2 w = *reinterpret_cast<const float2 *>(wp + 2 * n1 * C::BPF);
+                return make_float2(w.x * S.at(sb + 2 * n1 * C::BPF), w.y * S.at(sb + 2 * n1 * C::BPF + 1));
+              }, p1 + it * kGroupThreads);
             } else {
-              float *o = p.spec_out + row * N;
-              auto emit = [&](int k, float2 X) { o[k] = cabs_fast(X); };
-              if (tid == 0) fft_pass3_special<F>(fb, s_tw3, s_pt, emit);
-              else fft_pass3_unit<F>(u, fb + pa_off, fb + pb_off, s_tw3 + u, s_pt + u, emit);
+              fft_pass1<F>([&](int n1) {
+                float2 w = *reinterpret_cast<const float2 *>(wp + 2 * n1 * C::BPF);
+                const long long sa = sb + 2 * n1 * C::BPF, sc = sa + 1;
+                float xa = (sa >= 0 && sa < nsamp) ? S.at(sa) : 0.f;
+                float xb = (sc >= 0 && sc < nsamp) ? S.at(sc) : 0.f;
+                return make_float2(w.x * xa, w.y * xb);
+              }, p1 + it * kGroupThreads);
             }
           }
         }
-      }
-      group_bar(g);                          // all pass-3 reads done before the next pass 1 overwrites buf
-      if (MODE != MODE_LOGFILT) continue;
-      // ---------------- K2a: banded filterbank, contiguous slices -> partial sums ----------------
-      for (int s = tid; s < nseg; s += kGroupThreads) {
-        const Seg sg = s_segs[s];
-        const float *wp = s_fbw + sg.w0;
-        const float *mp = s_mags + sg.k0;
-        float acc[FPG][2];
-#pragma unroll
-        for (int fl = 0; fl < FPG; ++fl) acc[fl][0] = acc[fl][1] = 0.f;
-        int i = 0;
-        for (; i + 4 <= sg.cnt; i += 4) {
-          const float w0 = wp[i], w1 = wp[i + 1], w2 = wp[i + 2], w3 = wp[i + 3];
-#pragma unroll
-          for (int fl = 0; fl < FPG; ++fl) {
-            const float *m = mp + fl * mstride + i;
-            acc[fl][0] = fmaf(w0, m[0], acc[fl][0]);
-            acc[fl][1] = fmaf(w1, m[1], acc[fl][1]);
-            acc[fl][0] = fmaf(w2, m[2], acc[fl][0]);
-            acc[fl][1] = fmaf(w3, m[3], acc[fl][1]);
-          }
+        group_bar(g);
+        // ---------------- pass 2: twiddle, DFT16, in place ----------------
+        if (f + fl12 < f1) {
+#pragma unroll 1
+          for (int it = 0; it < C::IT12; ++it) fft_pass2<F>(tw2r, p2 + it * (kGroupThreads >> 4));
         }
-        for (; i < sg.cnt; ++i) {
-          const float w0 = wp[i];
-#pragma unroll
-          for (int fl = 0; fl < FPG; ++fl) acc[fl][0] = fmaf(w0, mp[fl * mstride + i], acc[fl][0]);
-        }
-#pragma unroll
-        for (int fl = 0; fl < FPG; ++fl) s_partial[fl * nseg + s] = acc[fl][0] + acc[fl][1];
-      }
-      group_bar(g);
-      // ---------------- K2b/K3: band sum, log10, lagged difference, stacked store ----------------
-      float fluxacc[FPG];
-#pragma unroll
-      for (int fl = 0; fl < FPG; ++fl) fluxacc[fl] = 0.f;
-      for (int j = tid; j < B; j += kGroupThreads) {
-        const int sb = s_bseg[j], se = s_bseg[j + 1];
-#pragma unroll
+        group_bar(g);
+        // ---------------- pass 3: last radix + real split (+ magnitude) ----------------
+#pragma unroll 1
         for (int fl = 0; fl < FPG; ++fl) {
           const int frame = f + fl;
+          if (frame >= f1) break;
+          const float2 *fbuf = buf + fl * C::BUF;
+          if (MODE == MODE_LOGFILT) {
+            float *mags = s_mags + (sub + fl) * mstride;
+            if (u != 0)
+              fft_pass3_unit<F>(u, fbuf + pa_off, fbuf + pb_off, s_tw3 + u, s_pt + u,
+                                [&](int k, float2 X) { mags[k] = cabs_fast(X); });
+            if (tid < 2 * R3) {   // the two self-paired columns: one bin per lane of warp 0
+              int bin;
+              const float2 X = fft_pass3_selfpaired<F>(tid, fbuf, s_wr, s_pt, bin);
+              mags[bin] = cabs_fast(X);
+            }
+          } else if (frame >= f0) {
+            const long long row = row0 + frame;
+            if (p.spec_complex) {
+              float2 *o = reinterpret_cast<float2 *>(p.spec_out) + row * N;
+              if (u != 0)
+                fft_pass3_unit<F>(u, fbuf + pa_off, fbuf + pb_off, s_tw3 + u, s_pt + u,
+                                  [&](int k, float2 X) { o[k] = X; });
+              if (tid < 2 * R3) {
+                int bin;
+                const float2 X = fft_pass3_selfpaired<F>(tid, fbuf, s_wr, s_pt, bin);
+                o[bin] = X;
+              }
+            } else {
+              float *o = p.spec_out + row * N;
+              if (u != 0)
+                fft_pass3_unit<F>(u, fbuf + pa_off, fbuf + pb_off, s_tw3 + u, s_pt + u,
+                                  [&](int k, float2 X) { o[k] = cabs_fast(X); });
+              if (tid < 2 * R3) {
+                int bin;
+                const float2 X = fft_pass3_selfpaired<F>(tid, fbuf, s_wr, s_pt, bin);
+                o[bin] = cabs_fast(X);
+              }
+            }
+          }
+        }
+        group_bar(g);   // pass-3 reads done before the next pass 1 overwrites buf; magnitudes visible
+      }
+      if (MODE != MODE_LOGFILT) continue;
+      // =============== K2a: banded filterbank for the TB frames at once ===============
+      for (int r = tid; r < p.nseg_pad; r += kGroupThreads) {
+        const int s = s_order[r];
+        if (s >= 0) {
+          const Seg sg = s_segs[s];
+          const float *wp = s_fbw + sg.w0;
+          const float *mp = s_mags + sg.k0;
+          float acc[TB];
+#pragma unroll
+          for (int t = 0; t < TB; ++t) acc[t] = 0.f;
+#pragma unroll 2
+          for (int i = 0; i < sg.cnt; ++i) {
+            const float w = wp[i];
+#pragma unroll
+            for (int t = 0; t < TB; ++t) acc[t] = fmaf(w, mp[t * mstride + i], acc[t]);
+          }
+#pragma unroll
+          for (int t = 0; t < TB; ++t) s_partial[t * nseg + s] = acc[t];
+        }
+      }
+      group_bar(g);
+      // =============== K2b/K3: band sum, log10, lagged difference, stacked store ===============
+      float fluxacc[TB];
+#pragma unroll
+      for (int t = 0; t < TB; ++t) fluxacc[t] = 0.f;
+      const int slot0 = kd > 0 ? fb % kd : 0;
+      for (int j = tid; j < B; j += kGroupThreads) {
+        const int sb = s_bseg[j], se = s_bseg[j + 1];
+        float *orow = p.out != nullptr ? p.out + (row0 + fb) * p.ld_out + j : nullptr;
+        int slot = slot0;
+#pragma unroll
+        for (int t = 0; t < TB; ++t) {
+          const int frame = fb + t;
           if (frame < f1) {
             float y = 0.f;
-            for (int s = sb; s < se; ++s) y += s_partial[fl * nseg + s];
-            float L = p.log_enabled ? log10f(__fadd_rn(__fmul_rn(p.mul, y), p.add)) : y;
+            for (int s = sb; s < se; ++s) y += s_partial[t * nseg + s];
+            float L = p.log_enabled ? __log10f(__fadd_rn(__fmul_rn(p.mul, y), p.add)) : y;
             float D = 0.f;
             if (kd > 0) {
-              const int slot = frame % kd;
               const float old = s_hist[slot * B + j];
               s_hist[slot * B + j] = L;
               if (frame >= kd) D = L - old;
               if (p.positive) D = fmaxf(D, 0.f);
+              slot = (slot + 1 == kd) ? 0 : slot + 1;
             }
-            if (p.num_classes > 0) s_lrow[fl * B + j] = L;
+            if (p.num_classes > 0) s_lrow[t * B + j] = L;
             if (frame >= f0) {
-              const long long row = row0 + frame;
-              if (p.out != nullptr) {
-                if (p.col_spec >= 0) p.out[row * p.ld_out + p.col_spec + j] = L;
-                if (p.col_diff >= 0) p.out[row * p.ld_out + p.col_diff + j] = D;
+              if (orow != nullptr) {
+                if (p.col_spec >= 0) orow[p.col_spec] = L;
+                if (p.col_diff >= 0) orow[p.col_diff] = D;
               }
-              fluxacc[fl] += D;
+              fluxacc[t] += D;
             }
           }
+          if (orow != nullptr) orow += p.ld_out;
         }
       }
       if (p.flux != nullptr || p.num_classes > 0) {
         if (p.flux != nullptr) {
 #pragma unroll
-          for (int fl = 0; fl < FPG; ++fl) {
-            float v = fluxacc[fl];
+          for (int t = 0; t < TB; ++t) {
+            float v = fluxacc[t];
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-            if ((tid & 31) == 0) s_red[fl * 4 + (tid >> 5)] = v;
+            if ((tid & 31) == 0) s_red[t * 4 + (tid >> 5)] = v;
           }
         }
         group_bar(g);
-        for (int fl = 0; fl < FPG; ++fl) {
-          const int frame = f + fl;
+        for (int t = 0; t < TB; ++t) {
+          const int frame = fb + t;
           if (frame < f0 || frame >= f1) continue;
           const long long row = row0 + frame;
           if (p.flux != nullptr && tid == 0)
-            p.flux[row] = (s_red[fl * 4] + s_red[fl * 4 + 1]) + (s_red[fl * 4 + 2] + s_red[fl * 4 + 3]);
+            p.flux[row] = (s_red[t * 4] + s_red[t * 4 + 1]) + (s_red[t * 4 + 2] + s_red[t * 4 + 3]);
           if (tid < p.num_classes) {
             float acc = 0.f;
             for (int i = p.proj_off[tid]; i < p.proj_off[tid + 1]; ++i)
-              acc = fmaf(__ldg(&p.proj_w[i]), s_lrow[fl * B + __ldg(&p.proj_band[i])], acc);
+              acc = fmaf(__ldg(&p.proj_w[i]), s_lrow[t * B + __ldg(&p.proj_band[i])], acc);
             p.proj[row * p.ld_proj + tid] = acc;
           }
         }
