@@ -65,7 +65,7 @@ struct ResPlan {
   // device tables
   float *d_window = nullptr;
   float2 *d_tw2 = nullptr, *d_tw3 = nullptr, *d_pt = nullptr, *d_wr = nullptr;
-  int *d_seg_order = nullptr;
+  int *d_woff = nullptr;
   float *d_fbw = nullptr;
   b2::Seg *d_segs = nullptr;
   int *d_bseg = nullptr;
@@ -191,19 +191,43 @@ int build_res(b200spec_plan *pl, const b200spec_res_desc &d, ResPlan &r) {
       s.k0 = d.band_start[j] + off;
       s.w0 = d.band_woff[j] + off;
       s.cnt = (L - off < chunk) ? L - off : chunk;
-      s.pad = 0;
+      s.slot = 0;
       segs.push_back(s);
     }
   }
   bseg[B] = (int)segs.size();
   r.nseg = (int)segs.size();
-  // processing order: longest slices first (stable), so every warp-round works on equal lengths
-  std::vector<int> order(segs.size());
-  for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return segs[a].cnt > segs[b].cnt; });
-  while (order.size() % b2::kGroupThreads) order.push_back(-1);
-  r.nseg_pad = (int)order.size();
-  if ((rc = upload(pl, order.data(), order.size(), &r.d_seg_order))) return rc;
+  // distribute the slices over the 128 threads of a group: longest-processing-time-first packing on
+  // (taps + a fixed per-slice cost); threads are then ordered by slice count so that the lanes of a
+  // warp run loops of similar shape.  Slot = original slice index (consecutive within a band).
+  for (size_t i = 0; i < segs.size(); ++i) segs[i].slot = (int)i;
+  {
+    const int NT = b2::kGroupThreads, kSliceCost = 4;
+    std::vector<int> order(segs.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return segs[a].cnt > segs[b].cnt; });
+    std::vector<std::vector<int>> bins(NT);
+    std::vector<int> load(NT, 0);
+    for (int s : order) {
+      int best = 0;
+      for (int t = 1; t < NT; ++t)
+        if (load[t] < load[best]) best = t;
+      bins[best].push_back(s);
+      load[best] += segs[s].cnt + kSliceCost;
+    }
+    std::vector<int> tord(NT);
+    for (int t = 0; t < NT; ++t) tord[t] = t;
+    std::stable_sort(tord.begin(), tord.end(), [&](int a, int b) { return bins[a].size() < bins[b].size(); });
+    std::vector<b2::Seg> work;
+    std::vector<int> woff(NT + 1, 0);
+    for (int t = 0; t < NT; ++t) {
+      woff[t] = (int)work.size();
+      for (int s : bins[tord[t]]) work.push_back(segs[s]);
+    }
+    woff[NT] = (int)work.size();
+    segs.swap(work);
+    if ((rc = upload(pl, woff.data(), woff.size(), &r.d_woff))) return rc;
+  }
   if ((rc = upload(pl, d.weights, (size_t)nnz, &r.d_fbw))) return rc;
   if ((rc = upload(pl, segs.data(), segs.size(), &r.d_segs))) return rc;
   if ((rc = upload(pl, bseg.data(), bseg.size(), &r.d_bseg))) return rc;
@@ -282,8 +306,7 @@ int launch_front(const b200spec_plan *pl, int res, int mode, const void *d_sig, 
   p.tw3 = r.d_tw3;
   p.pt = r.d_pt;
   p.wr = r.d_wr;
-  p.seg_order = r.d_seg_order;
-  p.nseg_pad = r.nseg_pad;
+  p.woff = r.d_woff;
   p.num_bands = r.num_bands;
   p.nnz = r.nnz;
   p.nseg = r.nseg;

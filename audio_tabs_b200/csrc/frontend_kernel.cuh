@@ -29,7 +29,7 @@ struct Seg {   // one contiguous slice of a filterbank band (odd length keeps la
   int k0;      // first FFT bin
   int w0;      // first weight index
   int cnt;     // number of taps
-  int pad;
+  int slot;    // partial-sum slot (slices of one band occupy consecutive slots)
 };
 
 struct FrontParams {
@@ -54,8 +54,7 @@ struct FrontParams {
   const float *fbw;
   const Seg *segs;
   const int *bseg;      // num_bands + 1
-  const int *seg_order; // nseg_pad: slices sorted by length (balanced warps), -1 = padding
-  int nseg_pad;
+  const int *woff;      // 129: thread t of a group works on slices [woff[t], woff[t+1]) of `segs`
   int log_enabled;
   float mul, add;
   int diff_frames, positive;
@@ -92,13 +91,13 @@ inline size_t front_smem_layout(FrontParams &p, int mode, int G) {
     p.o_fbw = (int)o;  o = al(o + sizeof(float) * p.nnz);
     p.o_segs = (int)o; o = al(o + sizeof(Seg) * p.nseg);
     p.o_bseg = (int)o; o = al(o + sizeof(int) * (p.num_bands + 1));
-    p.o_order = (int)o; o = al(o + sizeof(int) * p.nseg_pad);
+    p.o_order = (int)o; o = al(o + sizeof(int) * (kGroupThreads + 1));
   }
   p.o_groups = (int)o;
   size_t g = 0;
   g = al(g + sizeof(float2) * C::FPG * C::BUF);  // in-place FFT buffers
   p.g_mags = p.g_partial = p.g_hist = p.g_lrow = (int)g;
-  p.mag_stride = C::N + 4;
+  p.mag_stride = C::MS;
   if (mode == MODE_LOGFILT) {
     p.g_mags = (int)g;    g = al(g + sizeof(float) * C::TB * p.mag_stride);
     p.g_partial = (int)g; g = al(g + sizeof(float) * C::TB * p.nseg);
@@ -156,7 +155,7 @@ __device__ __forceinline__ const void *clip_base(const void *sig, long long off)
 template <int F, int IN, int MODE, int G>
 __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams p) {
   using C = FftCfg<F>;
-  constexpr int FPG = C::FPG, N = C::N, R3 = C::R3, S1 = C::S1, TB = C::TB;
+  constexpr int FPG = C::FPG, N = C::N, R3 = C::R3, S1 = C::S1, TB = C::TB, MS = C::MS;
   extern __shared__ __align__(16) unsigned char smem[];
   float *s_win = reinterpret_cast<float *>(smem + p.o_win);
   float2 *s_tw3 = reinterpret_cast<float2 *>(smem + p.o_tw3);
@@ -165,7 +164,7 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
   float *s_fbw = reinterpret_cast<float *>(smem + p.o_fbw);
   Seg *s_segs = reinterpret_cast<Seg *>(smem + p.o_segs);
   int *s_bseg = reinterpret_cast<int *>(smem + p.o_bseg);
-  int *s_order = reinterpret_cast<int *>(smem + p.o_order);
+  int *s_woff = reinterpret_cast<int *>(smem + p.o_order);
 
   for (int i = threadIdx.x; i < F; i += blockDim.x) s_win[i] = p.window[i];
   for (int i = threadIdx.x; i < C::TW3; i += blockDim.x) s_tw3[i] = p.tw3[i];
@@ -175,7 +174,7 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
     for (int i = threadIdx.x; i < p.nnz; i += blockDim.x) s_fbw[i] = p.fbw[i];
     for (int i = threadIdx.x; i < p.nseg; i += blockDim.x) s_segs[i] = p.segs[i];
     for (int i = threadIdx.x; i <= p.num_bands; i += blockDim.x) s_bseg[i] = p.bseg[i];
-    for (int i = threadIdx.x; i < p.nseg_pad; i += blockDim.x) s_order[i] = p.seg_order[i];
+    for (int i = threadIdx.x; i <= kGroupThreads; i += blockDim.x) s_woff[i] = p.woff[i];
   }
   __syncthreads();
 
@@ -200,7 +199,7 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
   float2 *p2 = buf + fl12 * C::BUF + (b12 & 15) * S1 + (b12 >> 4);      // pass-2 in-place base (k1, n3)
   const int u = tid;                                                    // pass-3 unit
   const int pa_off = fft_col_offset<F>(u), pb_off = fft_col_offset<F>((256 - u) & 255);
-  const int mstride = p.mag_stride;
+  const int wbeg = (MODE == MODE_LOGFILT) ? s_woff[tid] : 0, wend = (MODE == MODE_LOGFILT) ? s_woff[tid + 1] : 0;
 
   const int total_tasks = p.task_off[p.n_clips];
   const int B = p.num_bands, kd = p.diff_frames, nseg = p.nseg;
@@ -258,6 +257,17 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
             }
           }
         }
+        if (tid < 32) {
+          // one warp pulls the samples that only the NEXT step's frames touch into L1 (the rest of
+          // their windows overlaps what was just read), so pass 1 does not wait on L2/HBM
+          constexpr int ESZ = (IN == IN_F32_MONO) ? 4 : (IN == IN_F32_STEREO) ? 8 : (IN == IN_I16_MONO) ? 2 : 4;
+          const long long e0 = ((long long)((double)(f + FPG - 1) * p.hop) + (F / 2) - p.origin) * ESZ;
+          long long e1 = ((long long)((double)(f + 2 * FPG - 1) * p.hop) + (F / 2) - p.origin) * ESZ;
+          if (e1 > nsamp * ESZ) e1 = nsamp * ESZ;
+          const char *bytes = reinterpret_cast<const char *>(S.base);
+          for (long long a = (e0 & ~127LL) + tid * 128; a < e1; a += 32 * 128)
+            if (a >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(bytes + a));
+        }
         group_bar(g);
         // ---------------- pass 2: twiddle, DFT16, in place ----------------
         if (f + fl12 < f1) {
@@ -272,7 +282,7 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
           if (frame >= f1) break;
           const float2 *fbuf = buf + fl * C::BUF;
           if (MODE == MODE_LOGFILT) {
-            float *mags = s_mags + (sub + fl) * mstride;
+            float *mags = s_mags + (sub + fl) * MS;
             if (u != 0)
               fft_pass3_unit<F>(u, fbuf + pa_off, fbuf + pb_off, s_tw3 + u, s_pt + u,
                                 [&](int k, float2 X) { mags[k] = cabs_fast(X); });
@@ -310,24 +320,31 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
       }
       if (MODE != MODE_LOGFILT) continue;
       // =============== K2a: banded filterbank for the TB frames at once ===============
-      for (int r = tid; r < p.nseg_pad; r += kGroupThreads) {
-        const int s = s_order[r];
-        if (s >= 0) {
-          const Seg sg = s_segs[s];
-          const float *wp = s_fbw + sg.w0;
-          const float *mp = s_mags + sg.k0;
-          float acc[TB];
+      // every thread owns a list of slices with (nearly) the same total number of taps (host-side
+      // bin packing); two accumulator chains per frame hide the FFMA latency
+      for (int q = wbeg; q < wend; ++q) {
+        const Seg sg = s_segs[q];
+        const float *wp = s_fbw + sg.w0;
+        const float *mp = s_mags + sg.k0;
+        float a0[TB], a1[TB];
 #pragma unroll
-          for (int t = 0; t < TB; ++t) acc[t] = 0.f;
-#pragma unroll 2
-          for (int i = 0; i < sg.cnt; ++i) {
-            const float w = wp[i];
+        for (int t = 0; t < TB; ++t) a0[t] = a1[t] = 0.f;
+        int i = 0;
+        for (; i + 2 <= sg.cnt; i += 2) {
+          const float w0 = wp[i], w1v = wp[i + 1];
 #pragma unroll
-            for (int t = 0; t < TB; ++t) acc[t] = fmaf(w, mp[t * mstride + i], acc[t]);
+          for (int t = 0; t < TB; ++t) {
+            a0[t] = fmaf(w0, mp[t * MS + i], a0[t]);
+            a1[t] = fmaf(w1v, mp[t * MS + i + 1], a1[t]);
           }
-#pragma unroll
-          for (int t = 0; t < TB; ++t) s_partial[t * nseg + s] = acc[t];
         }
+        if (i < sg.cnt) {
+          const float w0 = wp[i];
+#pragma unroll
+          for (int t = 0; t < TB; ++t) a0[t] = fmaf(w0, mp[t * MS + i], a0[t]);
+        }
+#pragma unroll
+        for (int t = 0; t < TB; ++t) s_partial[t * nseg + sg.slot] = a0[t] + a1[t];
       }
       group_bar(g);
       // =============== K2b/K3: band sum, log10, lagged difference, stacked store ===============
@@ -339,12 +356,18 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
         const int sb = s_bseg[j], se = s_bseg[j + 1];
         float *orow = p.out != nullptr ? p.out + (row0 + fb) * p.ld_out + j : nullptr;
         int slot = slot0;
+        float ysum[TB];
+#pragma unroll
+        for (int t = 0; t < TB; ++t) ysum[t] = 0.f;
+        for (int s = sb; s < se; ++s) {
+#pragma unroll
+          for (int t = 0; t < TB; ++t) ysum[t] += s_partial[t * nseg + s];
+        }
 #pragma unroll
         for (int t = 0; t < TB; ++t) {
           const int frame = fb + t;
           if (frame < f1) {
-            float y = 0.f;
-            for (int s = sb; s < se; ++s) y += s_partial[t * nseg + s];
+            const float y = ysum[t];
             float L = p.log_enabled ? __log10f(__fadd_rn(__fmul_rn(p.mul, y), p.add)) : y;
             float D = 0.f;
             if (kd > 0) {
