@@ -8,7 +8,10 @@ namespace b2 {
 // groups of 128 threads per CTA for each frame size (bounded by shared memory and registers)
 template <int F>
 struct GroupsPerCta {
-  static constexpr int value = (F == 8192) ? 2 : 4;
+#ifndef B2_GROUPS
+#define B2_GROUPS 4
+#endif
+  static constexpr int value = (F == 8192) ? 2 : B2_GROUPS;
 };
 
 struct LaunchResult {

@@ -178,7 +178,12 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
   }
   __syncthreads();
 
-  const int g = threadIdx.x / kGroupThreads, tid = threadIdx.x % kGroupThreads;
+  // Warp w of every group lands on scheduler (SMSP) w.  Roles inside a group are not uniform (the
+  // self-paired columns run on virtual warp 0, the band stage uses the low warps), so the virtual
+  // warp index is rotated by the group number: the heavy roles of the G groups then sit on
+  // different schedulers instead of all on SMSP 0.
+  const int g = threadIdx.x / kGroupThreads;
+  const int tid = ((((threadIdx.x >> 5) + g) & 3) << 5) | (threadIdx.x & 31);
   unsigned char *gmem = smem + p.o_groups + (size_t)g * p.group_bytes;
   float2 *buf = reinterpret_cast<float2 *>(gmem);
   float *s_mags = reinterpret_cast<float *>(gmem + p.g_mags);
