@@ -237,11 +237,11 @@ class PitchClassProfileFilterbank(Filterbank):
     def __new__(cls, bin_frequencies, num_classes=12, fmin=100.0, fmax=5000.0, fref=A4):
         bin_frequencies = np.asarray(bin_frequencies, dtype=float)
         fb = np.zeros((len(bin_frequencies), num_classes))
-        with np.errstate(divide="ignore"):
+        with np.errstate(divide="ignore", invalid="ignore"):
             log_dev = np.log2(bin_frequencies / fref)
-        classes = np.round(num_classes * log_dev) % num_classes
-        rows = np.arange(len(fb))[1:]                    # bin 0 has no pitch
-        fb[rows, classes.astype(int)[1:]] = 1
+            classes = np.round(num_classes * log_dev) % num_classes
+        rows = np.arange(len(fb))[1:]                    # bin 0 (0 Hz) has no pitch
+        fb[rows, classes[1:].astype(int)] = 1
         fb[np.searchsorted(bin_frequencies, fmax, "right"):] = 0
         fb[:np.searchsorted(bin_frequencies, fmin)] = 0
         obj = Filterbank.__new__(cls, fb, bin_frequencies)

@@ -1,0 +1,265 @@
+"""GPU parity for every front end the reference reaches, the input formats, the batch engine and the
+edge cases (ragged / empty / tiny clips), all through the C ABI, against the oracle and the
+committed golden fixtures.  Tolerances: helpers.RTOL / ATOL (1e-4 / 1e-5)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from helpers import assert_close, assert_stft_close, noise
+from oracle import madmom_ref as ref
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).resolve().parent / "golden"
+SR = 44100
+
+
+@pytest.fixture(scope="module")
+def b2(cuda_device):
+    import audio_tabs_b200
+    return audio_tabs_b200
+
+
+# ---- golden fixtures ---------------------------------------------------------------------------
+def test_golden_beat_onset_logfilt(b2):
+    from audio_tabs_b200.frontends import rnn_beat_frontend_fused, rnn_onset_frontend
+    x = np.load(GOLD / "guitar_2s_f32.npy")
+    assert_close(rnn_beat_frontend_fused()(x), np.load(GOLD / "guitar_2s_beat314.npy"), what="golden beat")
+    assert_close(rnn_onset_frontend()(x), np.load(GOLD / "guitar_2s_onset266.npy"), what="golden onset")
+    chain = b2.SequentialProcessor((b2.SignalProcessor(num_channels=1, sample_rate=SR), b2.FramedSignalProcessor(),
+                                    b2.ShortTimeFourierTransformProcessor(),
+                                    b2.LogarithmicFilteredSpectrogramProcessor(num_bands=12, fmin=30, fmax=17000)))
+    assert_close(np.asarray(chain(x)), np.load(GOLD / "guitar_2s_logfilt81.npy"), what="golden logfilt")
+
+
+def test_golden_stft(b2):
+    x = np.load(GOLD / "guitar_2s_f32.npy")[:22050]
+    got = np.asarray(b2.ShortTimeFourierTransformProcessor()(b2.FramedSignal(b2.Signal(x, sample_rate=SR))))
+    assert_stft_close(got, np.load(GOLD / "guitar_0p5s_stft2048.npy"))
+
+
+def test_golden_real_audio_int16(b2):
+    """The reference's own recorded clip (int16): chroma/key front ends at 8192 and the beat front end."""
+    from audio_tabs_b200.audio.chroma import cnn_key_frontend, deep_chroma_frontend
+    from audio_tabs_b200.frontends import MultiResolutionFrontEnd, beat_specs
+    clip = np.load(GOLD / "refjob_3s_i16.npy")
+    assert_close(np.asarray(deep_chroma_frontend()(clip)), np.load(GOLD / "refjob_3s_deepchroma105.npy"), what="deepchroma")
+    assert_close(np.asarray(cnn_key_frontend()(clip)), np.load(GOLD / "refjob_3s_key105.npy"), what="key")
+    got = MultiResolutionFrontEnd(beat_specs(int16=True))(b2.Signal(clip, sample_rate=SR))
+    assert_close(got, np.load(GOLD / "refjob_3s_beat314.npy"), what="beat int16")
+    n, t = np.load(GOLD / "refjob_total_frames.npy")
+    assert len(b2.FramedSignal(b2.Signal(np.zeros(n, np.int16), sample_rate=SR))) == t == 1532
+
+
+# ---- chroma / key / chord front ends -------------------------------------------
+@pytest.mark.parametrize("which,width", [("deep_chroma_frontend", 105), ("cnn_key_frontend", 105),
+                                         ("cnn_chord_frontend", 113)])
+def test_8192_frontends_float(b2, which, width):
+    from audio_tabs_b200.audio import chroma
+    from audio_tabs_b200.synth import synth_guitar
+    x = synth_guitar(3000 + width, 8.0)
+    fps = 5 if which == "cnn_key_frontend" else 10
+    fmin, fmax = (60.0, 2600.0) if width == 113 else (65.0, 2100.0)
+    want = ref.log_filt_chain(8192, fps=fps, fmin=fmin, fmax=fmax)(x).data
+    got = np.asarray(getattr(chroma, which)()(x))
+    assert got.shape == want.shape == (8 * fps, width)
+    assert_close(got, want, what=which)
+
+
+@pytest.mark.parametrize("hop,fps", [(441.0, None), (None, 10)])
+def test_chord_chroma_config3(b2, hop, fps):
+    """BASELINE config 3: frame 4096 -> log filterbank (24 bpo, 65-2100 Hz, 87 bands) -> 12-bin chroma."""
+    from audio_tabs_b200.audio.chroma import chord_chroma_frontend
+    from audio_tabs_b200.synth import synth_guitar
+    x = synth_guitar(3003, 5.0)
+    kw = dict(hop_size=hop) if hop else dict(fps=fps)
+    spec = ref.log_filt_chain(4096, **({"hop_size": hop} if hop else {"fps": fps}))(x)
+    assert spec.data.shape[1] == 87
+    want = ref.fold_chroma(spec.data, spec.bin_frequencies)
+    got = np.asarray(chord_chroma_frontend(4096, **kw)(x))
+    assert got.shape == want.shape and got.shape[1] == 12
+    assert_close(got, want, what="folded chroma")
+
+
+def test_pitch_class_profile(b2):
+    x = noise(5, SR * 2)
+    stft = b2.ShortTimeFourierTransform(b2.FramedSignal(b2.Signal(x, sample_rate=SR), frame_size=4096))
+    got = np.asarray(b2.PitchClassProfile(b2.Spectrogram(stft)))
+    rs = ref.spectrogram(ref.ShortTimeFourierTransform(ref.FramedSignal(ref.Signal(x, sample_rate=SR), frame_size=4096)))
+    want, _ = ref.pitch_class_profile(rs)
+    assert_close(got, want.astype(np.float32), rtol=2e-4, atol=1e-4, what="pcp")
+
+
+# ---- unfused stages and stand-alone kernels ----------------------------------------------------
+def test_spectrogram_and_log_without_filterbank(b2):
+    x = noise(6, 30000)
+    fr = b2.FramedSignal(b2.Signal(x, sample_rate=SR), frame_size=1024)
+    rs = ref.spectrogram(ref.ShortTimeFourierTransform(ref.FramedSignal(ref.Signal(x, sample_rate=SR), frame_size=1024)))
+    got = np.asarray(b2.Spectrogram(b2.ShortTimeFourierTransform(fr)))
+    assert_close(got, rs.data, rtol=1e-4, atol=1e-5, what="magnitude")
+    got_log = np.asarray(b2.LogarithmicSpectrogram(b2.Spectrogram(b2.ShortTimeFourierTransform(fr)), mul=2, add=1))
+    assert_close(got_log, ref.logarithmic_spectrogram(rs, mul=2, add=1).data, what="log spec")
+    got_diff = np.asarray(b2.SpectrogramDifferenceProcessor(diff_frames=2, positive_diffs=True)(
+        b2.LogarithmicSpectrogram(b2.Spectrogram(b2.ShortTimeFourierTransform(fr)), mul=2, add=1)))
+    want_diff = ref.spectrogram_difference(ref.logarithmic_spectrogram(rs, mul=2, add=1).data, 2, positive_diffs=True)
+    assert_close(got_diff, want_diff, what="diff on raw bins")
+
+
+def test_standalone_stages_on_host_matrix(b2):
+    """A chain rooted at a caller-supplied magnitude matrix runs K2/K3 stand-alone."""
+    x = noise(8, 40000)
+    rs = ref.spectrogram(ref.ShortTimeFourierTransform(ref.FramedSignal(ref.Signal(x, sample_rate=SR), frame_size=2048)))
+    spec = b2.Spectrogram(rs.data, bin_frequencies=rs.bin_frequencies)
+    filt = b2.FilteredSpectrogram(spec, num_bands=12, fmin=30, fmax=17000)
+    rf = ref.filtered_spectrogram(rs, num_bands=12, fmin=30, fmax=17000)
+    assert_close(np.asarray(filt), rf.data, what="stand-alone filter")
+    log = b2.LogarithmicSpectrogram(b2.FilteredSpectrogram(spec, num_bands=12, fmin=30, fmax=17000), mul=1, add=1)
+    rl = ref.logarithmic_spectrogram(rf)
+    assert_close(np.asarray(log), rl.data, what="stand-alone filter+log")
+    d = b2.SpectrogramDifference(b2.LogarithmicSpectrogram(b2.FilteredSpectrogram(spec)), diff_frames=1,
+                                 positive_diffs=True)
+    assert_close(np.asarray(d), ref.spectrogram_difference(rl.data, 1, positive_diffs=True), what="stand-alone diff")
+
+
+def test_diff_only_and_unstacked(b2):
+    x = noise(9, SR)
+    mk = lambda stack: b2.SequentialProcessor((  # noqa: E731
+        b2.FramedSignalProcessor(frame_size=2048), b2.ShortTimeFourierTransformProcessor(),
+        b2.FilteredSpectrogramProcessor(num_bands=6), b2.LogarithmicSpectrogramProcessor(),
+        b2.SpectrogramDifferenceProcessor(diff_ratio=0.5, positive_diffs=False, stack_diffs=stack)))
+    sig = b2.Signal(x, sample_rate=SR)
+    spec = ref.log_filtered_spectrogram(x, frame_size=2048, num_bands=6)
+    want = ref.spectrogram_difference(spec, 1, positive_diffs=False)
+    assert_close(np.asarray(mk(None)(sig)), want, what="signed diff")
+    assert_close(np.asarray(mk(np.hstack)(sig)), np.hstack((spec, want)), what="hstack")
+    assert_close(np.asarray(mk(np.vstack)(sig)), np.vstack((spec, want)), what="custom stack fn")
+
+
+# ---- batch engine: formats, ragged batches, flux -----------------------------------------------
+def _oracle_beat(x):
+    return ref.rnn_beat_preprocessor()(x)
+
+
+def test_ragged_batch_with_empty_and_tiny_clips(b2):
+    from audio_tabs_b200.frontends import beat_specs
+    from audio_tabs_b200.plan import FrontEnd
+    from audio_tabs_b200.synth import synth_guitar
+    clips = [synth_guitar(4000, 1.3), np.zeros(0, np.float32), noise(1, 100), synth_guitar(4001, 0.77),
+             noise(2, 441), noise(3, 442), synth_guitar(4002, 2.05), noise(4, 1)]
+    fe = FrontEnd(beat_specs(), device=0)
+    outs = fe.process_batch(clips)
+    assert [o.shape[0] for o in outs] == [ref.num_frames_for(len(c), 441.0) for c in clips]
+    for c, o in zip(clips, outs):
+        assert o.shape[1] == 314
+        if len(c):
+            assert_close(o, _oracle_beat(c), what="ragged clip of %d samples" % len(c))
+    again = fe.process_batch(clips)
+    for a, b in zip(outs, again):
+        np.testing.assert_array_equal(a, b)                       # deterministic
+
+
+def test_stereo_downmix_float_and_int16(b2):
+    from audio_tabs_b200.frontends import beat_specs
+    from audio_tabs_b200.plan import FrontEnd
+    rng = np.random.default_rng(11)
+    st = (rng.standard_normal((30000, 2)) * 0.2).astype(np.float32)
+    out = FrontEnd(beat_specs(), device=0, channels=2).process_batch([st, st[:9000]])
+    assert_close(out[0], _oracle_beat(ref.Signal(st, sample_rate=SR, num_channels=1).data), what="stereo f32")
+    assert_close(out[1], _oracle_beat(ref.Signal(st[:9000], sample_rate=SR, num_channels=1).data), what="stereo f32 b")
+    sti = rng.integers(-20000, 20000, size=(25000, 2)).astype(np.int16)
+    outi = FrontEnd(beat_specs(int16=True), device=0, dtype="i16", channels=2).process_batch([sti])
+    assert_close(outi[0], _oracle_beat(ref.Signal(sti, sample_rate=SR, num_channels=1).data), what="stereo i16")
+    mono = FrontEnd(beat_specs(int16=True), device=0, dtype="i16").process_batch([sti[:, 0].copy()])
+    assert_close(mono[0], _oracle_beat(sti[:, 0].copy()), what="mono i16")
+
+
+def test_spectral_flux_and_projection_outputs(b2):
+    import torch
+    from audio_tabs_b200.frontends import log_filt_spec
+    from audio_tabs_b200.plan import FrontEnd
+    x = noise(12, SR * 2)
+    spec = log_filt_spec(2048, 441.0, 12, diff_ratio=0.5, fold=True)
+    fe = FrontEnd([spec], device=0)
+    packed = fe.pack([x, x[:20000]])
+    flux = torch.zeros(packed.total_frames, device="cuda")
+    proj = torch.zeros((packed.total_frames, 12), device="cuda")
+    out = fe.run_packed(packed, flux=[flux], proj=[proj]).cpu().numpy()
+    L = ref.log_filtered_spectrogram(x)
+    D = ref.spectrogram_difference(L, 1, positive_diffs=True)
+    T = L.shape[0]
+    assert_close(out[:T], np.hstack((L, D)), what="stacked")
+    np.testing.assert_allclose(flux.cpu().numpy()[:T], ref.spectral_flux(D), rtol=1e-4, atol=1e-4)
+    cf = ref.LogarithmicFilterbank(ref.fft_frequencies(1024, SR)).center_frequencies
+    assert_close(proj.cpu().numpy()[:T], ref.fold_chroma(L, cf), rtol=1e-4, atol=1e-4, what="projection")
+    L2 = ref.log_filtered_spectrogram(x[:20000])
+    D2 = ref.spectrogram_difference(L2, 1, positive_diffs=True)
+    assert_close(out[T:], np.hstack((L2, D2)), what="second clip restarts the diff")
+
+
+def test_pinned_pipeline_equals_resident_path(b2):
+    import torch
+    from audio_tabs_b200.frontends import beat_specs
+    from audio_tabs_b200.plan import FrontEnd
+    fe = FrontEnd(beat_specs(), device=0)
+    lens = [30000, 44100, 12345, 50000, 8000, 61000, 44100]
+    xs = [noise(100 + i, n) for i, n in enumerate(lens)]
+    packed = fe.pack(xs)
+    want = fe.run_packed(packed).cpu()
+    host_in = torch.from_numpy(np.concatenate(xs)).pin_memory()
+    host_out = torch.empty(want.shape, dtype=torch.float32).pin_memory()
+    fe.process_batch_pinned(host_in, lens, host_out, group_clips=2)
+    torch.cuda.synchronize()
+    assert torch.equal(host_out, want)
+
+
+def test_device_resident_signal_and_tensor_output(b2):
+    import torch
+    x = noise(13, 50000)
+    t = torch.from_numpy(x).cuda()
+    chain = b2.SequentialProcessor((b2.SignalProcessor(num_channels=1, sample_rate=SR), b2.FramedSignalProcessor(),
+                                    b2.ShortTimeFourierTransformProcessor(),
+                                    b2.LogarithmicFilteredSpectrogramProcessor()))
+    stage = chain(t)
+    dev = stage.tensor()
+    assert dev.is_cuda and dev.shape == (114, 81)
+    assert_close(dev.cpu().numpy(), ref.log_filtered_spectrogram(x), what="device signal")
+
+
+# ---- size-independent properties at BASELINE sizes ---------------------------------------------
+def test_properties_at_full_clip_length(b2):
+    """3-minute stems (BASELINE config 2 clip length): shapes, exact zeros, sign, determinism, and
+    agreement of the fused 3-resolution buffer with single-resolution launches (a checksum of checksums)."""
+    import torch
+    from audio_tabs_b200.frontends import beat_specs
+    from audio_tabs_b200.plan import FrontEnd, Packed
+    from audio_tabs_b200.synth import synth_batch_device
+    n = 180 * SR
+    dev = torch.device("cuda", 0)
+    sig = synth_batch_device(4, n, seed=5, device=dev)
+    sig[2 * n:3 * n] = 0                                            # one silent stem
+    specs = beat_specs()
+    fe = FrontEnd(specs, device=0)
+    packed = Packed(sig, [n] * 4, 441.0)
+    assert packed.num_frames == [18000] * 4
+    out = fe.run_packed(packed)
+    assert out.shape == (72000, 314) and bool(torch.isfinite(out).all())
+    assert not out[36000:54000].any()                              # log10(1 + 0) = 0, diff = 0
+    col = 0
+    for s in specs:
+        b, k = s.num_bands, s.diff_frames
+        d = out[:, col + b:col + 2 * b]
+        assert bool((d >= 0).all()) and bool((out[:, col:col + b] >= 0).all())
+        for c in range(4):
+            assert not d[c * 18000:c * 18000 + k].any()            # first k rows of every clip
+        single = FrontEnd([s], device=0).run_packed(packed)
+        assert torch.equal(single, out[:, col:col + 2 * b])
+        col += 2 * b
+    assert torch.equal(out, fe.run_packed(packed))                 # idempotent / deterministic
+    # linearity of the STFT under scaling by a power of two is exact
+    st1 = FrontEnd([specs[1]], device=0).stft_packed(Packed(sig[:n], [n], 441.0))
+    st2 = FrontEnd([specs[1]], device=0).stft_packed(Packed(sig[:n] * 0.5, [n], 441.0))
+    assert torch.equal(st1 * 0.5, st2)
+    # a spot check of the long clip against the oracle (first and last second)
+    x = sig[:n].cpu().numpy()
+    want_head = ref.rnn_beat_preprocessor()(x[:SR + 4096])[:90]
+    assert_close(out[:90].cpu().numpy(), want_head, what="head of 3-min stem")
