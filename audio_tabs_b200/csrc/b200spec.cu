@@ -65,9 +65,10 @@ struct ResPlan {
   // device tables
   float *d_window = nullptr;
   float2 *d_tw2 = nullptr, *d_tw3 = nullptr, *d_pt = nullptr, *d_wr = nullptr;
-  int *d_woff = nullptr;
+  int2 *d_fb_desc = nullptr;
+  float *d_fb_wt = nullptr;
+  int fb_bt = 9, fb_nb = 1;
   float *d_fbw = nullptr;
-  b2::Seg *d_segs = nullptr;
   int *d_bseg = nullptr;
   int *d_band_start = nullptr, *d_band_len = nullptr, *d_band_woff = nullptr;
   int *d_proj_off = nullptr, *d_proj_band = nullptr;
@@ -172,64 +173,71 @@ int build_res(b200spec_plan *pl, const b200spec_res_desc &d, ResPlan &r) {
   }
   r.nnz = nnz;
   r.kmax = kmax;
-  // every band is cut into contiguous slices of (about) nnz/128 taps; an ODD slice length keeps the
-  // lanes that work on neighbouring slices of one band on distinct shared-memory banks
-  int seg_max = (nnz + b2::kGroupThreads - 1) / b2::kGroupThreads;
-  if (seg_max < 9) seg_max = 9;
-  if (seg_max > 33) seg_max = 33;
-  seg_max |= 1;
-  std::vector<b2::Seg> segs;
-  std::vector<int> bseg(B + 1, 0);
-  for (int j = 0; j < B; ++j) {
-    bseg[j] = (int)segs.size();
-    const int L = d.band_len[j];
-    const int S = (L + seg_max - 1) / seg_max;
-    int chunk = S > 0 ? (L + S - 1) / S : 0;
-    if (S > 1) chunk |= 1;
-    for (int off = 0; off < L; off += chunk) {
-      b2::Seg s;
-      s.k0 = d.band_start[j] + off;
-      s.w0 = d.band_woff[j] + off;
-      s.cnt = (L - off < chunk) ? L - off : chunk;
-      s.slot = 0;
-      segs.push_back(s);
+  // Block stream (see fb_blocks in frontend_kernel.cuh): every band is padded with zero weights to a
+  // multiple of BT taps and cut into blocks; the 128 threads of a group each own NB consecutive
+  // blocks.  BT and NB are odd, so neighbouring lanes inside a band sit NB*BT (odd) bins apart and
+  // never share a shared-memory bank.  (BT, NB) minimises the per-thread instruction estimate.
+  const int NT = b2::kGroupThreads;
+  const int TB = 4096 / N;
+  int best_bt = 0, best_nb = 0;
+  long best_cost = -1;
+  for (int bt : {5, 7, 9}) {
+    long blocks = 0;
+    for (int j = 0; j < B; ++j) blocks += (d.band_len[j] + bt - 1) / bt;
+    int nb = (int)((blocks + NT - 1) / NT);
+    if (nb < 1) nb = 1;
+    nb |= 1;
+    const long cost = (long)nb * (3 + bt * (1 + 2 * TB));
+    if (best_cost < 0 || cost < best_cost) best_cost = cost, best_bt = bt, best_nb = nb;
+  }
+  if (best_nb > 31) return fail(B200SPEC_ERR_UNSUPPORTED, "filterbank with %d taps is too dense for the fused kernel", nnz);
+  const int BT = best_bt, NB = best_nb;
+  struct Block { int k0, band; const float *w; int len; };
+  std::vector<Block> stream;
+  for (int j = 0; j < B; ++j)
+    for (int off = 0; off < d.band_len[j]; off += BT)
+      stream.push_back({d.band_start[j] + off, j, d.weights + d.band_woff[j] + off,
+                        d.band_len[j] - off < BT ? d.band_len[j] - off : BT});
+  std::vector<int2> desc((size_t)NB * NT);
+  std::vector<float> wt((size_t)NB * BT * NT, 0.f);
+  std::vector<int> bseg(B + 1, -1);
+  int nslots = 0;
+  for (int t = 0; t < NT; ++t) {
+    int prev_band = -1;
+    for (int b = 0; b < NB; ++b) {
+      const size_t si = (size_t)t * NB + b;
+      int2 dsc;
+      if (si < stream.size()) {
+        const Block &blk = stream[si];
+        if (blk.band != prev_band) {          // a new (thread, band) piece -> a new partial-sum slot
+          if (bseg[blk.band] < 0) bseg[blk.band] = nslots;
+          ++nslots;
+          prev_band = blk.band;
+        }
+        const bool last = (b == NB - 1) || (si + 1 >= stream.size()) || (stream[si + 1].band != blk.band);
+        dsc.x = blk.k0;
+        dsc.y = (nslots - 1) | (last ? (int)0x80000000 : 0);
+        for (int i = 0; i < blk.len; ++i) wt[((size_t)b * BT + i) * NT + t] = blk.w[i];
+      } else {
+        dsc.x = 0;                             // idle block: zero weights, result goes to the dummy slot
+        dsc.y = -1;                            // patched to the dummy slot below
+        prev_band = -1;
+      }
+      desc[(size_t)b * NT + t] = dsc;
     }
   }
-  bseg[B] = (int)segs.size();
-  r.nseg = (int)segs.size();
-  // distribute the slices over the 128 threads of a group: longest-processing-time-first packing on
-  // (taps + a fixed per-slice cost); threads are then ordered by slice count so that the lanes of a
-  // warp run loops of similar shape.  Slot = original slice index (consecutive within a band).
-  for (size_t i = 0; i < segs.size(); ++i) segs[i].slot = (int)i;
-  {
-    const int NT = b2::kGroupThreads, kSliceCost = 4;
-    std::vector<int> order(segs.size());
-    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return segs[a].cnt > segs[b].cnt; });
-    std::vector<std::vector<int>> bins(NT);
-    std::vector<int> load(NT, 0);
-    for (int s : order) {
-      int best = 0;
-      for (int t = 1; t < NT; ++t)
-        if (load[t] < load[best]) best = t;
-      bins[best].push_back(s);
-      load[best] += segs[s].cnt + kSliceCost;
-    }
-    std::vector<int> tord(NT);
-    for (int t = 0; t < NT; ++t) tord[t] = t;
-    std::stable_sort(tord.begin(), tord.end(), [&](int a, int b) { return bins[a].size() < bins[b].size(); });
-    std::vector<b2::Seg> work;
-    std::vector<int> woff(NT + 1, 0);
-    for (int t = 0; t < NT; ++t) {
-      woff[t] = (int)work.size();
-      for (int s : bins[tord[t]]) work.push_back(segs[s]);
-    }
-    woff[NT] = (int)work.size();
-    segs.swap(work);
-    if ((rc = upload(pl, woff.data(), woff.size(), &r.d_woff))) return rc;
-  }
+  for (auto &dsc : desc)
+    if (dsc.y == -1) dsc.y = nslots | (int)0x80000000;
+  // bands without taps (or none at all) own an empty slot range
+  bseg[B] = nslots;
+  for (int j = B - 1; j >= 0; --j)
+    if (bseg[j] < 0) bseg[j] = bseg[j + 1];
+  r.nseg = nslots + 1;
+  r.fb_bt = BT;
+  r.fb_nb = NB;
   if ((rc = upload(pl, d.weights, (size_t)nnz, &r.d_fbw))) return rc;
-  if ((rc = upload(pl, segs.data(), segs.size(), &r.d_segs))) return rc;
+  if ((rc = upload(pl, desc.data(), desc.size(), &r.d_fb_desc))) return rc;
+  if ((rc = upload(pl, wt.data(), wt.size(), &r.d_fb_wt))) return rc;
   if ((rc = upload(pl, bseg.data(), bseg.size(), &r.d_bseg))) return rc;
   if ((rc = upload(pl, d.band_start, (size_t)B, &r.d_band_start))) return rc;
   if ((rc = upload(pl, d.band_len, (size_t)B, &r.d_band_len))) return rc;
@@ -306,13 +314,14 @@ int launch_front(const b200spec_plan *pl, int res, int mode, const void *d_sig, 
   p.tw3 = r.d_tw3;
   p.pt = r.d_pt;
   p.wr = r.d_wr;
-  p.woff = r.d_woff;
+  p.fb_desc = r.d_fb_desc;
+  p.fb_wt = r.d_fb_wt;
+  p.fb_bt = r.fb_bt;
+  p.fb_nb = r.fb_nb;
   p.num_bands = r.num_bands;
   p.nnz = r.nnz;
   p.nseg = r.nseg;
   p.kmax = r.kmax;
-  p.fbw = r.d_fbw;
-  p.segs = r.d_segs;
   p.bseg = r.d_bseg;
   p.log_enabled = r.log_enabled;
   p.mul = r.mul;

@@ -52,7 +52,7 @@ struct FftCfg {
   static constexpr int PT = 129 * R3;      // pt[k3*129 + q] = -i * W_F^(q + 256*k3)
   static constexpr int WR = 2 * R3;        // wr[e] = W_(2 R3)^e, used by the self-paired columns
   static constexpr int TB = 4096 / N;      // frames per tail batch (filterbank/log/diff stage)
-  static constexpr int MS = N + 4;         // floats per frame in the magnitude buffer
+  static constexpr int MS = N + 12;        // floats per frame in the magnitude buffer (+ room for padded taps)
 };
 
 // ---- complex helpers ---------------------------------------------------------------------------

@@ -25,13 +25,6 @@ namespace b2 {
 enum InputKind { IN_F32_MONO = 0, IN_F32_STEREO = 1, IN_I16_MONO = 2, IN_I16_STEREO = 3 };
 enum KernelMode { MODE_LOGFILT = 0, MODE_SPECTRUM = 1 };
 
-struct Seg {   // one contiguous slice of a filterbank band (odd length keeps lanes on distinct banks)
-  int k0;      // first FFT bin
-  int w0;      // first weight index
-  int cnt;     // number of taps
-  int slot;    // partial-sum slot (slices of one band occupy consecutive slots)
-};
-
 struct FrontParams {
   // input
   const void *sig;
@@ -50,11 +43,13 @@ struct FrontParams {
   const float2 *pt;     // [R3][129]  pt[k3*129 + q]  = -i W_F^(q + 256 k3)
   const float2 *wr;     // [2 R3]     wr[e] = W_(2 R3)^e
   // filterbank (MODE_LOGFILT)
-  int num_bands, nnz, nseg, kmax;
-  const float *fbw;
-  const Seg *segs;
-  const int *bseg;      // num_bands + 1
-  const int *woff;      // 129: thread t of a group works on slices [woff[t], woff[t+1]) of `segs`
+  // the banded filterbank as a block stream: every band is padded to a multiple of fb_bt taps, the
+  // stream is cut into blocks of fb_bt taps and thread t of a group owns blocks [t*fb_nb, (t+1)*fb_nb)
+  int num_bands, nnz, nseg, kmax;   // nseg = number of partial-sum slots (+1 dummy)
+  int fb_bt, fb_nb;                 // taps per block (5, 7 or 9) and blocks per thread (odd)
+  const int2 *fb_desc;  // [fb_nb][128]: {first bin, slot | flush << 31}
+  const float *fb_wt;   // [fb_nb * fb_bt][128]: tap-major weights (conflict-free across lanes)
+  const int *bseg;      // num_bands + 1: band j sums slots [bseg[j], bseg[j+1])
   int log_enabled;
   float mul, add;
   int diff_frames, positive;
@@ -88,10 +83,10 @@ inline size_t front_smem_layout(FrontParams &p, int mode, int G) {
   p.o_wr = (int)o;  o = al(o + sizeof(float2) * C::WR);
   p.o_fbw = p.o_segs = p.o_bseg = p.o_order = (int)o;
   if (mode == MODE_LOGFILT) {
-    p.o_fbw = (int)o;  o = al(o + sizeof(float) * p.nnz);
-    p.o_segs = (int)o; o = al(o + sizeof(Seg) * p.nseg);
+    p.o_fbw = (int)o;  o = al(o + sizeof(float) * p.fb_nb * p.fb_bt * kGroupThreads);   // tap-major weights
+    p.o_segs = (int)o; o = al(o + sizeof(int2) * p.fb_nb * kGroupThreads);                // block descriptors
     p.o_bseg = (int)o; o = al(o + sizeof(int) * (p.num_bands + 1));
-    p.o_order = (int)o; o = al(o + sizeof(int) * (kGroupThreads + 1));
+    p.o_order = (int)o;
   }
   p.o_groups = (int)o;
   size_t g = 0;
@@ -151,6 +146,42 @@ __device__ __forceinline__ const void *clip_base(const void *sig, long long off)
   return reinterpret_cast<const short2 *>(sig) + off;
 }
 
+// ---- K2a: banded filterbank on TB frames of magnitudes -----------------------------------------
+// desc[b*128 + t] = {first bin, slot | flush << 31}; wt[(b*BT + i)*128 + t] = weight of tap i.
+// Consecutive blocks of one band accumulate; the last block of a (thread, band) piece stores the
+// partial sum to its slot.  Padding taps carry weight 0 (they may read up to BT-1 bins past the band).
+template <int BT, int TB, int MS>
+__device__ __forceinline__ void fb_blocks(const int2 *__restrict__ s_desc, const float *__restrict__ s_wt,
+                                          const float *__restrict__ s_mags, float *__restrict__ s_partial,
+                                          int nb, int pstride, int tid) {
+  float a0[TB], a1[TB];
+#pragma unroll
+  for (int t = 0; t < TB; ++t) a0[t] = a1[t] = 0.f;
+  const int2 *dp = s_desc + tid;
+  const float *wp = s_wt + tid;
+  for (int b = 0; b < nb; ++b, dp += kGroupThreads, wp += BT * kGroupThreads) {
+    const int2 d = *dp;
+    const float *mp = s_mags + d.x;
+#pragma unroll
+    for (int i = 0; i < BT; ++i) {
+      const float w = wp[i * kGroupThreads];
+#pragma unroll
+      for (int t = 0; t < TB; ++t) {
+        if (i & 1) a1[t] = fmaf(w, mp[t * MS + i], a1[t]);
+        else a0[t] = fmaf(w, mp[t * MS + i], a0[t]);
+      }
+    }
+    if (d.y < 0) {
+      const int slot = d.y & 0x7fffffff;
+#pragma unroll
+      for (int t = 0; t < TB; ++t) {
+        s_partial[t * pstride + slot] = a0[t] + a1[t];
+        a0[t] = a1[t] = 0.f;
+      }
+    }
+  }
+}
+
 // ---- the front-end kernel ----------------------------------------------------------------------
 template <int F, int IN, int MODE, int G>
 __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams p) {
@@ -161,20 +192,23 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
   float2 *s_tw3 = reinterpret_cast<float2 *>(smem + p.o_tw3);
   float2 *s_pt = reinterpret_cast<float2 *>(smem + p.o_pt);
   float2 *s_wr = reinterpret_cast<float2 *>(smem + p.o_wr);
-  float *s_fbw = reinterpret_cast<float *>(smem + p.o_fbw);
-  Seg *s_segs = reinterpret_cast<Seg *>(smem + p.o_segs);
+  float *s_wt = reinterpret_cast<float *>(smem + p.o_fbw);
+  int2 *s_desc = reinterpret_cast<int2 *>(smem + p.o_segs);
   int *s_bseg = reinterpret_cast<int *>(smem + p.o_bseg);
-  int *s_woff = reinterpret_cast<int *>(smem + p.o_order);
 
   for (int i = threadIdx.x; i < F; i += blockDim.x) s_win[i] = p.window[i];
   for (int i = threadIdx.x; i < C::TW3; i += blockDim.x) s_tw3[i] = p.tw3[i];
   for (int i = threadIdx.x; i < C::PT; i += blockDim.x) s_pt[i] = p.pt[i];
   for (int i = threadIdx.x; i < C::WR; i += blockDim.x) s_wr[i] = p.wr[i];
   if (MODE == MODE_LOGFILT) {
-    for (int i = threadIdx.x; i < p.nnz; i += blockDim.x) s_fbw[i] = p.fbw[i];
-    for (int i = threadIdx.x; i < p.nseg; i += blockDim.x) s_segs[i] = p.segs[i];
+    for (int i = threadIdx.x; i < p.fb_nb * p.fb_bt * kGroupThreads; i += blockDim.x) s_wt[i] = p.fb_wt[i];
+    for (int i = threadIdx.x; i < p.fb_nb * kGroupThreads; i += blockDim.x) s_desc[i] = p.fb_desc[i];
     for (int i = threadIdx.x; i <= p.num_bands; i += blockDim.x) s_bseg[i] = p.bseg[i];
-    for (int i = threadIdx.x; i <= kGroupThreads; i += blockDim.x) s_woff[i] = p.woff[i];
+    // magnitudes (and their padding, which zero-weight taps may read) start out finite
+    float *allmags = reinterpret_cast<float *>(smem + p.o_groups);
+    for (int gi = 0; gi < G; ++gi)
+      for (int i = threadIdx.x; i < TB * MS; i += blockDim.x)
+        reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(allmags) + (size_t)gi * p.group_bytes + p.g_mags)[i] = 0.f;
   }
   __syncthreads();
 
@@ -204,7 +238,6 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
   float2 *p2 = buf + fl12 * C::BUF + (b12 & 15) * S1 + (b12 >> 4);      // pass-2 in-place base (k1, n3)
   const int u = tid;                                                    // pass-3 unit
   const int pa_off = fft_col_offset<F>(u), pb_off = fft_col_offset<F>((256 - u) & 255);
-  const int wbeg = (MODE == MODE_LOGFILT) ? s_woff[tid] : 0, wend = (MODE == MODE_LOGFILT) ? s_woff[tid + 1] : 0;
 
   const int total_tasks = p.task_off[p.n_clips];
   const int B = p.num_bands, kd = p.diff_frames, nseg = p.nseg;
@@ -325,32 +358,12 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
       }
       if (MODE != MODE_LOGFILT) continue;
       // =============== K2a: banded filterbank for the TB frames at once ===============
-      // every thread owns a list of slices with (nearly) the same total number of taps (host-side
-      // bin packing); two accumulator chains per frame hide the FFMA latency
-      for (int q = wbeg; q < wend; ++q) {
-        const Seg sg = s_segs[q];
-        const float *wp = s_fbw + sg.w0;
-        const float *mp = s_mags + sg.k0;
-        float a0[TB], a1[TB];
-#pragma unroll
-        for (int t = 0; t < TB; ++t) a0[t] = a1[t] = 0.f;
-        int i = 0;
-        for (; i + 2 <= sg.cnt; i += 2) {
-          const float w0 = wp[i], w1v = wp[i + 1];
-#pragma unroll
-          for (int t = 0; t < TB; ++t) {
-            a0[t] = fmaf(w0, mp[t * MS + i], a0[t]);
-            a1[t] = fmaf(w1v, mp[t * MS + i + 1], a1[t]);
-          }
-        }
-        if (i < sg.cnt) {
-          const float w0 = wp[i];
-#pragma unroll
-          for (int t = 0; t < TB; ++t) a0[t] = fmaf(w0, mp[t * MS + i], a0[t]);
-        }
-#pragma unroll
-        for (int t = 0; t < TB; ++t) s_partial[t * nseg + sg.slot] = a0[t] + a1[t];
-      }
+      // every thread runs the same fb_nb blocks of fb_bt taps (zero-padded weights): no divergence, no
+      // loop bookkeeping, tap-major weights and an odd bin stride between lanes keep every access
+      // conflict free
+      if (p.fb_bt == 5) fb_blocks<5, TB, MS>(s_desc, s_wt, s_mags, s_partial, p.fb_nb, nseg, tid);
+      else if (p.fb_bt == 7) fb_blocks<7, TB, MS>(s_desc, s_wt, s_mags, s_partial, p.fb_nb, nseg, tid);
+      else fb_blocks<9, TB, MS>(s_desc, s_wt, s_mags, s_partial, p.fb_nb, nseg, tid);
       group_bar(g);
       // =============== K2b/K3: band sum, log10, lagged difference, stacked store ===============
       float fluxacc[TB];
