@@ -27,7 +27,7 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
     "-DB200SPEC_BUILD",
-]
+] + os.environ.get("B200SPEC_EXTRA_NVCC_FLAGS", "").split()   # e.g. -DB2_GROUPS=3 for tuning experiments
 
 
 def _nvcc() -> str:

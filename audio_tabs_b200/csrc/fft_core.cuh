@@ -56,8 +56,22 @@ struct FftCfg {
 };
 
 // ---- complex helpers ---------------------------------------------------------------------------
+// On sm_100 a complex add/subtract is ONE packed-FP32 instruction (FADD2 / FFMA2 on a 64-bit
+// register pair) instead of two scalar ones; the host build (tests/emu) uses the scalar form.
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000) && !defined(B2_NO_PACKED_F32)
+#define B2_PACKED_F32 1
+B2_HD float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+B2_HD float2 csub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
+B2_HD float2 cadd_conj(float2 a, float2 b) { return __ffma2_rn(b, make_float2(1.f, -1.f), a); }   // a + conj(b)
+B2_HD float2 csub_conj(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, 1.f), a); }   // a - conj(b)
+B2_HD float2 emul(float2 a, float2 b) { return __fmul2_rn(a, b); }                                   // element-wise
+#else
 B2_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 B2_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+B2_HD float2 cadd_conj(float2 a, float2 b) { return make_float2(a.x + b.x, a.y - b.y); }
+B2_HD float2 csub_conj(float2 a, float2 b) { return make_float2(a.x - b.x, a.y + b.y); }
+B2_HD float2 emul(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+#endif
 B2_HD float2 cmul(float2 a, float2 b) {
   return make_float2(fmaf(a.x, b.x, -(a.y * b.y)), fmaf(a.x, b.y, a.y * b.x));
 }
@@ -81,11 +95,11 @@ B2_HD void dft2(float2 &a, float2 &b) {
 // natural order in, natural order out
 B2_HD void dft4(float2 &x0, float2 &x1, float2 &x2, float2 &x3) {
   float2 t0 = cadd(x0, x2), t1 = csub(x0, x2);
-  float2 t2 = cadd(x1, x3), t3 = mul_neg_i(csub(x1, x3));
+  float2 t2 = cadd(x1, x3), d = csub(x1, x3);   // t3 = -i d = (d.y, -d.x), applied component-wise
   x0 = cadd(t0, t2);
   x2 = csub(t0, t2);
-  x1 = cadd(t1, t3);
-  x3 = csub(t1, t3);
+  x1 = make_float2(t1.x + d.y, t1.y - d.x);
+  x3 = make_float2(t1.x - d.y, t1.y + d.x);
 }
 
 // in place; X[k] ends up at v[pos8(k)]
@@ -192,8 +206,8 @@ B2_HD void fft_pass3_unit(int u, const float2 *pa, const float2 *pb, const float
   for (int n3 = 0; n3 < R3; ++n3) {
     float2 a = pa[n3];
     float2 b = pb[n3];
-    P[n3] = make_float2(a.x + b.x, a.y - b.y);  // a + conj(b)
-    M[n3] = make_float2(a.x - b.x, a.y + b.y);  // a - conj(b)
+    P[n3] = cadd_conj(a, b);  // a + conj(b)
+    M[n3] = csub_conj(a, b);  // a - conj(b)
   }
 #pragma unroll
   for (int n3 = 1; n3 < R3; ++n3) {

@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
             if (interior) {
               fft_pass1<F>([&](int n1) {
                 float2 w = *reinterpret_cast<const float2 *>(wp + 2 * n1 * C::BPF);
-                return make_float2(w.x * S.at(sb + 2 * n1 * C::BPF), w.y * S.at(sb + 2 * n1 * C::BPF + 1));
+                return emul(w, make_float2(S.at(sb + 2 * n1 * C::BPF), S.at(sb + 2 * n1 * C::BPF + 1)));
               }, p1 + it * kGroupThreads);
             } else {
               fft_pass1<F>([&](int n1) {
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
                 const long long sa = sb + 2 * n1 * C::BPF, sc = sa + 1;
                 float xa = (sa >= 0 && sa < nsamp) ? S.at(sa) : 0.f;
                 float xb = (sc >= 0 && sc < nsamp) ? S.at(sc) : 0.f;
-                return make_float2(w.x * xa, w.y * xb);
+                return emul(w, make_float2(xa, xb));
               }, p1 + it * kGroupThreads);
             }
           }
