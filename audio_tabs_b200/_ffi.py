@@ -89,6 +89,7 @@ SYMBOLS = [
                                             C.c_int64, C.POINTER(OutDesc), C.c_void_p]),
     ("b200spec_plan_num_res", C.c_int, [C.c_void_p]),
     ("b200spec_plan_num_bands", C.c_int, [C.c_void_p, C.c_int32]),
+    ("b200spec_plan_filterbank_layout", C.c_int, [C.c_void_p, C.c_int32, c_int32_p]),
     ("b200spec_launch_count", C.c_int64, []),
 ]
 

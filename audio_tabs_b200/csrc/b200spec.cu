@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "aux_kernels.cuh"
+#include "fb_pack.h"
 #include "front_inst.cuh"
 
 namespace {
@@ -57,7 +58,7 @@ struct ResPlan {
   int frame_size = 0;
   double hop = 0;
   int origin = 0;
-  int num_bands = 0, nnz = 0, nseg = 0, nseg_pad = 0, kmax = 0;
+  int num_bands = 0, nnz = 0, kmax = 0;
   int log_enabled = 0;
   float mul = 1.f, add = 1.f;
   int diff_frames = 0, positive = 0;
@@ -65,11 +66,11 @@ struct ResPlan {
   // device tables
   float *d_window = nullptr;
   float2 *d_tw2 = nullptr, *d_tw3 = nullptr, *d_pt = nullptr, *d_wr = nullptr;
-  int2 *d_fb_desc = nullptr;
-  float *d_fb_wt = nullptr;
-  int fb_bt = 9, fb_nb = 1;
+  int fb_L = 3, fb_ns = 1, fb_kmin = 0, fb_ndw = 0, fb_ndirect = 0, fb_w4_global = 0;
+  float4 *d_fb_w4 = nullptr;
+  int4 *d_fb_band = nullptr;
+  float *d_fb_dw = nullptr;
   float *d_fbw = nullptr;
-  int *d_bseg = nullptr;
   int *d_band_start = nullptr, *d_band_len = nullptr, *d_band_woff = nullptr;
   int *d_proj_off = nullptr, *d_proj_band = nullptr;
   float *d_proj_w = nullptr;
@@ -173,72 +174,38 @@ int build_res(b200spec_plan *pl, const b200spec_res_desc &d, ResPlan &r) {
   }
   r.nnz = nnz;
   r.kmax = kmax;
-  // Block stream (see fb_blocks in frontend_kernel.cuh): every band is padded with zero weights to a
-  // multiple of BT taps and cut into blocks; the 128 threads of a group each own NB consecutive
-  // blocks.  BT and NB are odd, so neighbouring lanes inside a band sit NB*BT (odd) bins apart and
-  // never share a shared-memory bank.  (BT, NB) minimises the per-thread instruction estimate.
-  const int NT = b2::kGroupThreads;
-  const int TB = 4096 / N;
-  int best_bt = 0, best_nb = 0;
-  long best_cost = -1;
-  for (int bt : {5, 7, 9}) {
-    long blocks = 0;
-    for (int j = 0; j < B; ++j) blocks += (d.band_len[j] + bt - 1) / bt;
-    int nb = (int)((blocks + NT - 1) / NT);
-    if (nb < 1) nb = 1;
-    nb |= 1;
-    const long cost = (long)nb * (3 + bt * (1 + 2 * TB));
-    if (best_cost < 0 || cost < best_cost) best_cost = cost, best_bt = bt, best_nb = nb;
-  }
-  if (best_nb > 31) return fail(B200SPEC_ERR_UNSUPPORTED, "filterbank with %d taps is too dense for the fused kernel", nnz);
-  const int BT = best_bt, NB = best_nb;
-  struct Block { int k0, band; const float *w; int len; };
-  std::vector<Block> stream;
-  for (int j = 0; j < B; ++j)
-    for (int off = 0; off < d.band_len[j]; off += BT)
-      stream.push_back({d.band_start[j] + off, j, d.weights + d.band_woff[j] + off,
-                        d.band_len[j] - off < BT ? d.band_len[j] - off : BT});
-  std::vector<int2> desc((size_t)NB * NT);
-  std::vector<float> wt((size_t)NB * BT * NT, 0.f);
-  std::vector<int> bseg(B + 1, -1);
-  int nslots = 0;
-  for (int t = 0; t < NT; ++t) {
-    int prev_band = -1;
-    for (int b = 0; b < NB; ++b) {
-      const size_t si = (size_t)t * NB + b;
-      int2 dsc;
-      if (si < stream.size()) {
-        const Block &blk = stream[si];
-        if (blk.band != prev_band) {          // a new (thread, band) piece -> a new partial-sum slot
-          if (bseg[blk.band] < 0) bseg[blk.band] = nslots;
-          ++nslots;
-          prev_band = blk.band;
-        }
-        const bool last = (b == NB - 1) || (si + 1 >= stream.size()) || (stream[si + 1].band != blk.band);
-        dsc.x = blk.k0;
-        dsc.y = (nslots - 1) | (last ? (int)0x80000000 : 0);
-        for (int i = 0; i < blk.len; ++i) wt[((size_t)b * BT + i) * NT + t] = blk.w[i];
-      } else {
-        dsc.x = 0;                             // idle block: zero weights, result goes to the dummy slot
-        dsc.y = -1;                            // patched to the dummy slot below
-        prev_band = -1;
-      }
-      desc[(size_t)b * NT + t] = dsc;
+  // slab form of the filterbank for the fused kernel (fb_pack.h)
+  const int TBF = F == 1024 ? b2::FftCfg<1024>::TBF : F == 2048 ? b2::FftCfg<2048>::TBF : F == 4096 ? b2::FftCfg<4096>::TBF : b2::FftCfg<8192>::TBF;
+  b2::FbPack fp = b2::fb_pack(N, B, d.band_start, d.band_len, d.band_woff, d.weights, TBF);
+  {  // does the weight table fit next to everything else the kernel keeps in shared memory?
+    b2::FrontParams probe{};
+    probe.num_bands = B;
+    probe.fb_L = fp.L;
+    probe.fb_ns = fp.NS;
+    probe.fb_ndw = (int)fp.dw.size();
+    probe.diff_frames = d.diff_frames;
+    size_t need = 0;
+    switch (F) {
+      case 1024: need = b2::front_smem_layout<1024>(probe, b2::MODE_LOGFILT, b2::GroupsPerCta<1024>::value); break;
+      case 2048: need = b2::front_smem_layout<2048>(probe, b2::MODE_LOGFILT, b2::GroupsPerCta<2048>::value); break;
+      case 4096: need = b2::front_smem_layout<4096>(probe, b2::MODE_LOGFILT, b2::GroupsPerCta<4096>::value); break;
+      default: need = b2::front_smem_layout<8192>(probe, b2::MODE_LOGFILT, b2::GroupsPerCta<8192>::value); break;
+    }
+    if (need > b2::kMaxSmemPerCta) {   // keep the table in global memory (one fixed slab length)
+      fp = b2::fb_pack(N, B, d.band_start, d.band_len, d.band_woff, d.weights, TBF, 15);
+      r.fb_w4_global = 1;
     }
   }
-  for (auto &dsc : desc)
-    if (dsc.y == -1) dsc.y = nslots | (int)0x80000000;
-  // bands without taps (or none at all) own an empty slot range
-  bseg[B] = nslots;
-  for (int j = B - 1; j >= 0; --j)
-    if (bseg[j] < 0) bseg[j] = bseg[j + 1];
-  r.nseg = nslots + 1;
-  r.fb_bt = BT;
-  r.fb_nb = NB;
+  r.fb_L = fp.L;
+  r.fb_ns = fp.NS;
+  r.fb_kmin = fp.kmin;
+  r.fb_ndw = (int)fp.dw.size();
+  r.fb_ndirect = fp.ndirect;
+  static_assert(sizeof(b2::FbBand) == sizeof(int4), "FbBand must match the int4 the kernel reads");
   if ((rc = upload(pl, d.weights, (size_t)nnz, &r.d_fbw))) return rc;
-  if ((rc = upload(pl, desc.data(), desc.size(), &r.d_fb_desc))) return rc;
-  if ((rc = upload(pl, wt.data(), wt.size(), &r.d_fb_wt))) return rc;
-  if ((rc = upload(pl, bseg.data(), bseg.size(), &r.d_bseg))) return rc;
+  if ((rc = upload(pl, reinterpret_cast<const float4 *>(fp.w4.data()), fp.w4.size() / 4, &r.d_fb_w4))) return rc;
+  if ((rc = upload(pl, reinterpret_cast<const int4 *>(fp.band.data()), fp.band.size(), &r.d_fb_band))) return rc;
+  if ((rc = upload(pl, fp.dw.data(), fp.dw.size(), &r.d_fb_dw))) return rc;
   if ((rc = upload(pl, d.band_start, (size_t)B, &r.d_band_start))) return rc;
   if ((rc = upload(pl, d.band_len, (size_t)B, &r.d_band_len))) return rc;
   if ((rc = upload(pl, d.band_woff, (size_t)B, &r.d_band_woff))) return rc;
@@ -314,15 +281,17 @@ int launch_front(const b200spec_plan *pl, int res, int mode, const void *d_sig, 
   p.tw3 = r.d_tw3;
   p.pt = r.d_pt;
   p.wr = r.d_wr;
-  p.fb_desc = r.d_fb_desc;
-  p.fb_wt = r.d_fb_wt;
-  p.fb_bt = r.fb_bt;
-  p.fb_nb = r.fb_nb;
+  p.fb_w4 = r.d_fb_w4;
+  p.fb_band = r.d_fb_band;
+  p.fb_dw = r.d_fb_dw;
+  p.fb_L = r.fb_L;
+  p.fb_ns = r.fb_ns;
+  p.fb_kmin = r.fb_kmin;
+  p.fb_ndw = r.fb_ndw;
+  p.fb_w4_global = r.fb_w4_global;
   p.num_bands = r.num_bands;
   p.nnz = r.nnz;
-  p.nseg = r.nseg;
   p.kmax = r.kmax;
-  p.bseg = r.d_bseg;
   p.log_enabled = r.log_enabled;
   p.mul = r.mul;
   p.add = r.add;
@@ -341,6 +310,9 @@ int launch_front(const b200spec_plan *pl, int res, int mode, const void *d_sig, 
     case 4096: e = b2_launch_front_4096(in, mode, p, pl->num_sms, task_bound, st); break;
     default: e = b2_launch_front_8192(in, mode, p, pl->num_sms, task_bound, st); break;
   }
+  if (e == cudaErrorInvalidConfiguration)
+    return fail(B200SPEC_ERR_UNSUPPORTED, "the fused kernel for frame size %d with this filterbank (%d bands) needs more "
+                "shared memory than an SM has; use the unfused stft / filter_log calls", r.frame_size, r.num_bands);
   if (e != cudaSuccess) return fail(B200SPEC_ERR_CUDA, "front-end kernel launch failed: %s", cudaGetErrorString(e));
   g_launches++;
   return 0;
@@ -531,6 +503,18 @@ int b200spec_plan_num_res(const b200spec_plan *plan) { return plan ? plan->num_r
 int b200spec_plan_num_bands(const b200spec_plan *plan, int32_t res) {
   if (!plan || res < 0 || res >= plan->num_res) return -1;
   return plan->res[res].num_bands;
+}
+
+int b200spec_plan_filterbank_layout(const b200spec_plan *plan, int32_t res, int32_t out[6]) {
+  if (!plan || !out || res < 0 || res >= plan->num_res) return fail(B200SPEC_ERR_ARG, "plan/out is NULL or res out of range");
+  const ResPlan &r = plan->res[res];
+  out[0] = r.fb_L;
+  out[1] = r.fb_ns;
+  out[2] = r.fb_kmin;
+  out[3] = r.kmax;
+  out[4] = r.fb_ndirect;
+  out[5] = r.fb_ndw;
+  return 0;
 }
 
 int64_t b200spec_launch_count(void) { return g_launches.load(); }

@@ -1,0 +1,97 @@
+// fb_core.cuh -- the two thread-level pieces of the fused filterbank stage (K2): slab sums and the
+// per-band gather.  __host__ __device__ so tests/emu can run the exact thread mapping on the CPU
+// (test infrastructure only; the product path is the CUDA build).  Packing: fb_pack.h.
+//
+// Replaces np.dot(spec, filterbank) of madmom.audio.spectrogram.FilteredSpectrogram (reached from
+// /root/reference/backend/app/services/grid/beats.py:74).
+#pragma once
+#include "fft_core.cuh"
+
+#if !defined(__CUDACC__)
+struct float4 {
+  float x, y, z, w;
+};
+struct int4 {
+  int x, y, z, w;
+};
+static inline float4 make_float4(float x, float y, float z, float w) {
+  float4 r;
+  r.x = x; r.y = y; r.z = z; r.w = w;
+  return r;
+}
+#endif
+
+namespace b2 {
+
+// Thread `tid` walks the L consecutive bins of each of its slabs once, for TBF frames at a time:
+// one 128-bit weight load per bin (shared by the frames), one magnitude load per bin and frame, four
+// FMAs per bin and frame.  Neighbouring lanes sit L (odd) bins apart: no bank conflicts, no
+// descriptors, no data-dependent control flow.  s_part[t * pstride + 4 * slab + r] receives the sum
+// for the band with index r modulo 4.
+// W4G: the weight table did not fit in shared memory and is read from global memory (read-only path).
+template <int L, int TBF, int MS, bool W4G = false>
+B2_HD void fb_slabs(const float4 *s_w4, const float *s_mags, float *s_part, int ns, int kmin, int pstride, int tid) {
+  for (int s = 0; s < ns; ++s) {
+    const int g = s * kGroupThreads + tid;
+    int k0 = kmin + g * L;
+    if (k0 > MS - L) k0 = MS - L;                // slabs past the spectrum carry zero weights
+    const float4 *wp = s_w4 + s * L * kGroupThreads + tid;
+    const float *mp = s_mags + k0;
+    float4 acc[TBF];
+#pragma unroll
+    for (int t = 0; t < TBF; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+#if defined(__CUDA_ARCH__)
+      const float4 w = W4G ? __ldg(wp + i * kGroupThreads) : wp[i * kGroupThreads];
+#else
+      const float4 w = wp[i * kGroupThreads];
+#endif
+#pragma unroll
+      for (int t = 0; t < TBF; ++t) {
+        const float m = mp[t * MS + i];
+        acc[t].x = fmaf(w.x, m, acc[t].x);
+        acc[t].y = fmaf(w.y, m, acc[t].y);
+        acc[t].z = fmaf(w.z, m, acc[t].z);
+        acc[t].w = fmaf(w.w, m, acc[t].w);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < TBF; ++t) reinterpret_cast<float4 *>(s_part + t * pstride)[g] = acc[t];
+  }
+}
+
+template <int TBF, int MS>
+B2_HD void fb_slabs_dispatch(int L, const float4 *s_w4, const float *s_mags, float *s_part, int ns, int kmin,
+                             int pstride, int tid) {
+  switch (L) {
+    case 3: fb_slabs<3, TBF, MS>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
+    case 5: fb_slabs<5, TBF, MS>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
+    case 7: fb_slabs<7, TBF, MS>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
+    case 9: fb_slabs<9, TBF, MS>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
+    case 11: fb_slabs<11, TBF, MS>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
+    case 13: fb_slabs<13, TBF, MS>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
+    default: fb_slabs<15, TBF, MS>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
+  }
+}
+
+// band sums of TBF frames for the band described by bd (FbBand in fb_pack.h)
+template <int TBF, int MS>
+B2_HD void fb_band_sum(const int4 bd, const float *s_part, int pstride, const float *s_mags, const float *s_dw,
+                       float (&ysum)[TBF]) {
+#pragma unroll
+  for (int t = 0; t < TBF; ++t) ysum[t] = 0.f;
+  const float *pp = s_part + bd.x;
+  for (int i = 0; i < bd.y; ++i) {               // slab band: partial sums of the slabs it touches
+#pragma unroll
+    for (int t = 0; t < TBF; ++t) ysum[t] += pp[t * pstride + 4 * i];
+  }
+  const float *dm = s_mags + bd.z;
+  for (int i = 0; i < bd.w; ++i) {               // direct band: its few taps straight from the magnitudes
+    const float w = s_dw[bd.x + i];
+#pragma unroll
+    for (int t = 0; t < TBF; ++t) ysum[t] = fmaf(w, dm[t * MS + i], ysum[t]);
+  }
+}
+
+}  // namespace b2

@@ -51,8 +51,14 @@ struct FftCfg {
   static constexpr int TW3 = 129 * R3;     // tw3[n3*129 + q] = W_N^(n3*q), q in [0,128]
   static constexpr int PT = 129 * R3;      // pt[k3*129 + q] = -i * W_F^(q + 256*k3)
   static constexpr int WR = 2 * R3;        // wr[e] = W_(2 R3)^e, used by the self-paired columns
-  static constexpr int TB = 4096 / N;      // frames per tail batch (filterbank/log/diff stage)
-  static constexpr int MS = N + 12;        // floats per frame in the magnitude buffer (+ room for padded taps)
+  // frames per tail batch (filterbank/log/diff stage): 4, 4, 2, 1 -- measured best on B200 (profiles/README.md)
+#ifdef B2_TAIL_STEPS
+  static constexpr int TB = (F == 8192) ? 1 : B2_TAIL_STEPS * FPG;
+#else
+  static constexpr int TB = (F == 1024) ? 4 : (F == 2048) ? 4 : (F == 4096) ? 2 : 1;
+#endif
+  static constexpr int TBF = TB < 4 ? TB : 4;                        // frames per filterbank / band-stage call
+  static constexpr int MS = N + 16;        // floats per frame in the magnitude buffer (+ room for the last slab)
 };
 
 // ---- complex helpers ---------------------------------------------------------------------------

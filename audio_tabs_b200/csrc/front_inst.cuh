@@ -14,6 +14,8 @@ struct GroupsPerCta {
   static constexpr int value = (F == 8192) ? 2 : B2_GROUPS;
 };
 
+constexpr size_t kMaxSmemPerCta = 227 * 1024;   // opt-in dynamic shared memory per CTA on sm_100
+
 struct LaunchResult {
   cudaError_t err;
   int launches;
@@ -23,6 +25,7 @@ template <int F, int IN, int MODE>
 static cudaError_t launch_one(FrontParams &p, int num_sms, long long task_bound, cudaStream_t st) {
   constexpr int G = GroupsPerCta<F>::value;
   const size_t smem = front_smem_layout<F>(p, MODE, G);
+  if (smem > kMaxSmemPerCta) return cudaErrorInvalidConfiguration;   // reported as "unsupported" by the caller
   auto kern = k_front<F, IN, MODE, G>;
   // per device and cheap; set on every launch so multi-device processes stay correct
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

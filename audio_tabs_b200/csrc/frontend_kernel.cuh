@@ -18,7 +18,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "fb_core.cuh"
 #include "fft_core.cuh"
+#include "tma.cuh"
 
 namespace b2 {
 
@@ -42,14 +44,16 @@ struct FrontParams {
   const float2 *tw3;    // [R3][129]  tw3[n3*129 + q] = W_N^(n3 q)
   const float2 *pt;     // [R3][129]  pt[k3*129 + q]  = -i W_F^(q + 256 k3)
   const float2 *wr;     // [2 R3]     wr[e] = W_(2 R3)^e
-  // filterbank (MODE_LOGFILT)
-  // the banded filterbank as a block stream: every band is padded to a multiple of fb_bt taps, the
-  // stream is cut into blocks of fb_bt taps and thread t of a group owns blocks [t*fb_nb, (t+1)*fb_nb)
-  int num_bands, nnz, nseg, kmax;   // nseg = number of partial-sum slots (+1 dummy)
-  int fb_bt, fb_nb;                 // taps per block (5, 7 or 9) and blocks per thread (odd)
-  const int2 *fb_desc;  // [fb_nb][128]: {first bin, slot | flush << 31}
-  const float *fb_wt;   // [fb_nb * fb_bt][128]: tap-major weights (conflict-free across lanes)
-  const int *bseg;      // num_bands + 1: band j sums slots [bseg[j], bseg[j+1])
+  // filterbank (MODE_LOGFILT), slab form: the used bins [fb_kmin, kmax) are cut into slabs of fb_L
+  // (odd) consecutive bins; thread t of a group owns slabs t, t + 128, ... (fb_ns of them) and keeps
+  // four running sums per frame, one per band index modulo 4 (a slab never touches two bands with
+  // the same index modulo 4; bands too narrow for that are "direct" and summed in the band stage)
+  int num_bands, nnz, kmax;
+  int fb_L, fb_ns, fb_kmin, fb_ndw;
+  int fb_w4_global;      // 1: fb_w4 stays in global memory (too large for shared memory; fb_L is 15 then)
+  const float4 *fb_w4;   // [fb_ns][fb_L][128]: weights of bin i of thread t's slab, by band index & 3
+  const int4 *fb_band;   // per band: slab band {first partial, count, 0, 0}; direct band {dw offset, 0, first bin, taps}
+  const float *fb_dw;    // weights of the direct bands
   int log_enabled;
   float mul, add;
   int diff_frames, positive;
@@ -67,9 +71,10 @@ struct FrontParams {
   float *spec_out;      // (rows, N) float or float2
   int spec_complex;
   // shared-memory carve-up (byte offsets), filled by front_smem_layout()
-  int o_win, o_tw3, o_pt, o_wr, o_fbw, o_segs, o_bseg, o_order, o_groups, group_bytes;
+  int o_win, o_tw3, o_pt, o_wr, o_w4, o_band, o_dw, o_groups, group_bytes;
   int g_mags, g_partial, g_hist, g_lrow, g_red, g_task;  // offsets inside a group's block
   int mag_stride;                                        // floats per frame in the magnitude buffer
+  int part_stride;                                       // floats per frame in the partial-sum buffer
 };
 
 template <int F>
@@ -81,12 +86,12 @@ inline size_t front_smem_layout(FrontParams &p, int mode, int G) {
   p.o_tw3 = (int)o; o = al(o + sizeof(float2) * C::TW3);
   p.o_pt = (int)o;  o = al(o + sizeof(float2) * C::PT);
   p.o_wr = (int)o;  o = al(o + sizeof(float2) * C::WR);
-  p.o_fbw = p.o_segs = p.o_bseg = p.o_order = (int)o;
+  p.o_w4 = p.o_band = p.o_dw = (int)o;
+  p.part_stride = p.fb_ns * kGroupThreads * 4;
   if (mode == MODE_LOGFILT) {
-    p.o_fbw = (int)o;  o = al(o + sizeof(float) * p.fb_nb * p.fb_bt * kGroupThreads);   // tap-major weights
-    p.o_segs = (int)o; o = al(o + sizeof(int2) * p.fb_nb * kGroupThreads);                // block descriptors
-    p.o_bseg = (int)o; o = al(o + sizeof(int) * (p.num_bands + 1));
-    p.o_order = (int)o;
+    p.o_w4 = (int)o;   o = al(o + (p.fb_w4_global ? 16 : sizeof(float4) * p.fb_ns * p.fb_L * kGroupThreads));
+    p.o_band = (int)o; o = al(o + sizeof(int4) * (p.num_bands > 0 ? p.num_bands : 1));
+    p.o_dw = (int)o;   o = al(o + sizeof(float) * (p.fb_ndw > 0 ? p.fb_ndw : 1));
   }
   p.o_groups = (int)o;
   size_t g = 0;
@@ -95,14 +100,18 @@ inline size_t front_smem_layout(FrontParams &p, int mode, int G) {
   p.mag_stride = C::MS;
   if (mode == MODE_LOGFILT) {
     p.g_mags = (int)g;    g = al(g + sizeof(float) * C::TB * p.mag_stride);
-    p.g_partial = (int)g; g = al(g + sizeof(float) * C::TB * p.nseg);
+    p.g_partial = (int)g; g = al(g + sizeof(float) * C::TBF * p.part_stride);
     p.g_hist = (int)g;    g = al(g + sizeof(float) * (p.diff_frames > 0 ? p.diff_frames : 1) * p.num_bands);
-    p.g_lrow = (int)g;    g = al(g + sizeof(float) * C::TB * p.num_bands);
+    p.g_lrow = (int)g;    g = al(g + sizeof(float) * C::TBF * p.num_bands);
   }
-  p.g_red = (int)g;  g = al(g + sizeof(float) * 4 * C::TB);
+  p.g_red = (int)g;  g = al(g + sizeof(float) * 4 * C::TBF);
   p.g_task = (int)g; g = al(g + 16);
   p.group_bytes = (int)g;
+#ifdef B2_SMEM_PAD   // tuning experiment: shrink the L1 carve-out by this many bytes
+  return o + g * G + B2_SMEM_PAD;
+#else
   return o + g * G;
+#endif
 }
 
 #if defined(__CUDACC__)
@@ -146,64 +155,29 @@ __device__ __forceinline__ const void *clip_base(const void *sig, long long off)
   return reinterpret_cast<const short2 *>(sig) + off;
 }
 
-// ---- K2a: banded filterbank on TB frames of magnitudes -----------------------------------------
-// desc[b*128 + t] = {first bin, slot | flush << 31}; wt[(b*BT + i)*128 + t] = weight of tap i.
-// Consecutive blocks of one band accumulate; the last block of a (thread, band) piece stores the
-// partial sum to its slot.  Padding taps carry weight 0 (they may read up to BT-1 bins past the band).
-template <int BT, int TB, int MS>
-__device__ __forceinline__ void fb_blocks(const int2 *__restrict__ s_desc, const float *__restrict__ s_wt,
-                                          const float *__restrict__ s_mags, float *__restrict__ s_partial,
-                                          int nb, int pstride, int tid) {
-  float a0[TB], a1[TB];
-#pragma unroll
-  for (int t = 0; t < TB; ++t) a0[t] = a1[t] = 0.f;
-  const int2 *dp = s_desc + tid;
-  const float *wp = s_wt + tid;
-  for (int b = 0; b < nb; ++b, dp += kGroupThreads, wp += BT * kGroupThreads) {
-    const int2 d = *dp;
-    const float *mp = s_mags + d.x;
-#pragma unroll
-    for (int i = 0; i < BT; ++i) {
-      const float w = wp[i * kGroupThreads];
-#pragma unroll
-      for (int t = 0; t < TB; ++t) {
-        if (i & 1) a1[t] = fmaf(w, mp[t * MS + i], a1[t]);
-        else a0[t] = fmaf(w, mp[t * MS + i], a0[t]);
-      }
-    }
-    if (d.y < 0) {
-      const int slot = d.y & 0x7fffffff;
-#pragma unroll
-      for (int t = 0; t < TB; ++t) {
-        s_partial[t * pstride + slot] = a0[t] + a1[t];
-        a0[t] = a1[t] = 0.f;
-      }
-    }
-  }
-}
-
 // ---- the front-end kernel ----------------------------------------------------------------------
 template <int F, int IN, int MODE, int G>
 __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams p) {
   using C = FftCfg<F>;
-  constexpr int FPG = C::FPG, N = C::N, R3 = C::R3, S1 = C::S1, TB = C::TB, MS = C::MS;
+  constexpr int FPG = C::FPG, N = C::N, R3 = C::R3, S1 = C::S1, TB = C::TB, TBF = C::TBF, MS = C::MS;
   extern __shared__ __align__(16) unsigned char smem[];
   float *s_win = reinterpret_cast<float *>(smem + p.o_win);
   float2 *s_tw3 = reinterpret_cast<float2 *>(smem + p.o_tw3);
   float2 *s_pt = reinterpret_cast<float2 *>(smem + p.o_pt);
   float2 *s_wr = reinterpret_cast<float2 *>(smem + p.o_wr);
-  float *s_wt = reinterpret_cast<float *>(smem + p.o_fbw);
-  int2 *s_desc = reinterpret_cast<int2 *>(smem + p.o_segs);
-  int *s_bseg = reinterpret_cast<int *>(smem + p.o_bseg);
+  float4 *s_w4 = reinterpret_cast<float4 *>(smem + p.o_w4);
+  int4 *s_band = reinterpret_cast<int4 *>(smem + p.o_band);
+  float *s_dw = reinterpret_cast<float *>(smem + p.o_dw);
 
   for (int i = threadIdx.x; i < F; i += blockDim.x) s_win[i] = p.window[i];
   for (int i = threadIdx.x; i < C::TW3; i += blockDim.x) s_tw3[i] = p.tw3[i];
   for (int i = threadIdx.x; i < C::PT; i += blockDim.x) s_pt[i] = p.pt[i];
   for (int i = threadIdx.x; i < C::WR; i += blockDim.x) s_wr[i] = p.wr[i];
   if (MODE == MODE_LOGFILT) {
-    for (int i = threadIdx.x; i < p.fb_nb * p.fb_bt * kGroupThreads; i += blockDim.x) s_wt[i] = p.fb_wt[i];
-    for (int i = threadIdx.x; i < p.fb_nb * kGroupThreads; i += blockDim.x) s_desc[i] = p.fb_desc[i];
-    for (int i = threadIdx.x; i <= p.num_bands; i += blockDim.x) s_bseg[i] = p.bseg[i];
+    if (!p.fb_w4_global)
+      for (int i = threadIdx.x; i < p.fb_ns * p.fb_L * kGroupThreads; i += blockDim.x) s_w4[i] = p.fb_w4[i];
+    for (int i = threadIdx.x; i < p.num_bands; i += blockDim.x) s_band[i] = p.fb_band[i];
+    for (int i = threadIdx.x; i < p.fb_ndw; i += blockDim.x) s_dw[i] = p.fb_dw[i];
     // magnitudes (and their padding, which zero-weight taps may read) start out finite
     float *allmags = reinterpret_cast<float *>(smem + p.o_groups);
     for (int gi = 0; gi < G; ++gi)
@@ -216,8 +190,13 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
   // self-paired columns run on virtual warp 0, the band stage uses the low warps), so the virtual
   // warp index is rotated by the group number: the heavy roles of the G groups then sit on
   // different schedulers instead of all on SMSP 0.
+#ifdef B2_GROUP_BY_SMSP   // tuning experiment: all four warps of a group on one scheduler
+  const int g = (threadIdx.x >> 5) % G;
+  const int tid = (((threadIdx.x >> 5) / G) << 5) | (threadIdx.x & 31);
+#else
   const int g = threadIdx.x / kGroupThreads;
   const int tid = ((((threadIdx.x >> 5) + g) & 3) << 5) | (threadIdx.x & 31);
+#endif
   unsigned char *gmem = smem + p.o_groups + (size_t)g * p.group_bytes;
   float2 *buf = reinterpret_cast<float2 *>(gmem);
   float *s_mags = reinterpret_cast<float *>(gmem + p.g_mags);
@@ -240,7 +219,7 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
   const int pa_off = fft_col_offset<F>(u), pb_off = fft_col_offset<F>((256 - u) & 255);
 
   const int total_tasks = p.task_off[p.n_clips];
-  const int B = p.num_bands, kd = p.diff_frames, nseg = p.nseg;
+  const int B = p.num_bands, kd = p.diff_frames, pstride = p.part_stride;
 
   for (;;) {
     if (tid == 0) *s_task = atomicAdd(p.task_counter, 1);
@@ -265,6 +244,7 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
     const int fs = (MODE == MODE_LOGFILT && kd > 0) ? max(0, f0 - kd) : f0;  // warm-up rows for the diff
     Samples<IN> S{clip_base<IN>(p.sig, samp0)};
 
+    int hslot = (MODE == MODE_LOGFILT && kd > 0) ? fs % kd : 0;   // difference ring slot of frame f
     for (int fb = fs; fb < f1; fb += TB) {
       // =============== FFT of the TB frames of this tail batch, FPG frames per step ===============
 #pragma unroll 1
@@ -274,24 +254,26 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
         // ---------------- pass 1: frame load * window, DFT16 ----------------
         if (f + fl12 < f1) {
           const long long s0 = (long long)((double)(f + fl12) * p.hop) - (F / 2) - p.origin;
-          const bool interior = (s0 >= 0) && (s0 + F <= nsamp);
+          {
+            const bool interior = (s0 >= 0) && (s0 + F <= nsamp);
 #pragma unroll 1
-          for (int it = 0; it < C::IT12; ++it) {
-            const long long sb = s0 + 2 * (b12 + it * kGroupThreads);
-            const float *wp = w1 + 2 * it * kGroupThreads;
-            if (interior) {
-              fft_pass1<F>([&](int n1) {
-                float2 w = *reinterpret_cast<const float2 *>(wp + 2 * n1 * C::BPF);
-                return emul(w, make_float2(S.at(sb + 2 * n1 * C::BPF), S.at(sb + 2 * n1 * C::BPF + 1)));
-              }, p1 + it * kGroupThreads);
-            } else {
-              fft_pass1<F>([&](int n1) {
-                float2 w = *reinterpret_cast<const float2 *>(wp + 2 * n1 * C::BPF);
-                const long long sa = sb + 2 * n1 * C::BPF, sc = sa + 1;
-                float xa = (sa >= 0 && sa < nsamp) ? S.at(sa) : 0.f;
-                float xb = (sc >= 0 && sc < nsamp) ? S.at(sc) : 0.f;
-                return emul(w, make_float2(xa, xb));
-              }, p1 + it * kGroupThreads);
+            for (int it = 0; it < C::IT12; ++it) {
+              const long long sb = s0 + 2 * (b12 + it * kGroupThreads);
+              const float *wp = w1 + 2 * it * kGroupThreads;
+              if (interior) {
+                fft_pass1<F>([&](int n1) {
+                  float2 w = *reinterpret_cast<const float2 *>(wp + 2 * n1 * C::BPF);
+                  return emul(w, make_float2(S.at(sb + 2 * n1 * C::BPF), S.at(sb + 2 * n1 * C::BPF + 1)));
+                }, p1 + it * kGroupThreads);
+              } else {
+                fft_pass1<F>([&](int n1) {
+                  float2 w = *reinterpret_cast<const float2 *>(wp + 2 * n1 * C::BPF);
+                  const long long sa = sb + 2 * n1 * C::BPF, sc = sa + 1;
+                  float xa = (sa >= 0 && sa < nsamp) ? S.at(sa) : 0.f;
+                  float xb = (sc >= 0 && sc < nsamp) ? S.at(sc) : 0.f;
+                  return emul(w, make_float2(xa, xb));
+                }, p1 + it * kGroupThreads);
+              }
             }
           }
         }
@@ -354,81 +336,106 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
             }
           }
         }
-        group_bar(g);   // pass-3 reads done before the next pass 1 overwrites buf; magnitudes visible
+        group_bar(g);   // pass-3 reads done: buf is free again; magnitudes visible
       }
-      if (MODE != MODE_LOGFILT) continue;
-      // =============== K2a: banded filterbank for the TB frames at once ===============
-      // every thread runs the same fb_nb blocks of fb_bt taps (zero-padded weights): no divergence, no
-      // loop bookkeeping, tap-major weights and an odd bin stride between lanes keep every access
-      // conflict free
-      if (p.fb_bt == 5) fb_blocks<5, TB, MS>(s_desc, s_wt, s_mags, s_partial, p.fb_nb, nseg, tid);
-      else if (p.fb_bt == 7) fb_blocks<7, TB, MS>(s_desc, s_wt, s_mags, s_partial, p.fb_nb, nseg, tid);
-      else fb_blocks<9, TB, MS>(s_desc, s_wt, s_mags, s_partial, p.fb_nb, nseg, tid);
-      group_bar(g);
-      // =============== K2b/K3: band sum, log10, lagged difference, stacked store ===============
-      float fluxacc[TB];
-#pragma unroll
-      for (int t = 0; t < TB; ++t) fluxacc[t] = 0.f;
-      const int slot0 = kd > 0 ? fb % kd : 0;
-      for (int j = tid; j < B; j += kGroupThreads) {
-        const int sb = s_bseg[j], se = s_bseg[j + 1];
-        float *orow = p.out != nullptr ? p.out + (row0 + fb) * p.ld_out + j : nullptr;
-        int slot = slot0;
-        float ysum[TB];
-#pragma unroll
-        for (int t = 0; t < TB; ++t) ysum[t] = 0.f;
-        for (int s = sb; s < se; ++s) {
-#pragma unroll
-          for (int t = 0; t < TB; ++t) ysum[t] += s_partial[t * nseg + s];
-        }
-#pragma unroll
-        for (int t = 0; t < TB; ++t) {
-          const int frame = fb + t;
-          if (frame < f1) {
-            const float y = ysum[t];
-            float L = p.log_enabled ? __log10f(__fadd_rn(__fmul_rn(p.mul, y), p.add)) : y;
-            float D = 0.f;
-            if (kd > 0) {
-              const float old = s_hist[slot * B + j];
-              s_hist[slot * B + j] = L;
-              if (frame >= kd) D = L - old;
-              if (p.positive) D = fmaxf(D, 0.f);
-              slot = (slot + 1 == kd) ? 0 : slot + 1;
-            }
-            if (p.num_classes > 0) s_lrow[t * B + j] = L;
-            if (frame >= f0) {
-              if (orow != nullptr) {
-                if (p.col_spec >= 0) orow[p.col_spec] = L;
-                if (p.col_diff >= 0) orow[p.col_diff] = D;
-              }
-              fluxacc[t] += D;
-            }
-          }
-          if (orow != nullptr) orow += p.ld_out;
-        }
-      }
-      if (p.flux != nullptr || p.num_classes > 0) {
-        if (p.flux != nullptr) {
-#pragma unroll
-          for (int t = 0; t < TB; ++t) {
-            float v = fluxacc[t];
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-            if ((tid & 31) == 0) s_red[t * 4 + (tid >> 5)] = v;
-          }
-        }
+      // =============== tail for the TB frames of this batch, TBF at a time ===============
+      if (MODE == MODE_LOGFILT)
+#pragma unroll 1
+      for (int h = 0; h < TB; h += TBF) {
+        const int fh = fb + h;
+        if (fh >= f1) break;
+        if (h > 0) group_bar(g);                     // the previous sub-batch is done with s_partial
+        const float *hmags = s_mags + h * MS;
+        // ---- K2a: slab filterbank ----
+        if (p.fb_w4_global) fb_slabs<15, TBF, MS, true>(p.fb_w4, hmags, s_partial, p.fb_ns, p.fb_kmin, pstride, tid);
+        else fb_slabs_dispatch<TBF, MS>(p.fb_L, s_w4, hmags, s_partial, p.fb_ns, p.fb_kmin, pstride, tid);
         group_bar(g);
-        for (int t = 0; t < TB; ++t) {
-          const int frame = fb + t;
-          if (frame < f0 || frame >= f1) continue;
-          const long long row = row0 + frame;
-          if (p.flux != nullptr && tid == 0)
-            p.flux[row] = (s_red[t * 4] + s_red[t * 4 + 1]) + (s_red[t * 4 + 2] + s_red[t * 4 + 3]);
-          if (tid < p.num_classes) {
-            float acc = 0.f;
-            for (int i = p.proj_off[tid]; i < p.proj_off[tid + 1]; ++i)
-              acc = fmaf(__ldg(&p.proj_w[i]), s_lrow[t * B + __ldg(&p.proj_band[i])], acc);
-            p.proj[row * p.ld_proj + tid] = acc;
+        // ---- K2b/K3: band sum, log10, lagged difference, stacked store ----
+        // lane = band.  Trip counts are made warp-uniform (REDUX max) and lanes past their own count
+        // add 0, so the gather loops carry no divergence.
+        float fluxacc[TBF];
+#pragma unroll
+        for (int t = 0; t < TBF; ++t) fluxacc[t] = 0.f;
+        for (int jb = 0; jb < B; jb += kGroupThreads) {
+          const int j = jb + tid;
+          const bool valid = j < B;
+          const int4 bd = valid ? s_band[j] : make_int4(0, 0, 0, 0);
+          const int nP = __reduce_max_sync(0xffffffffu, bd.y), nD = __reduce_max_sync(0xffffffffu, bd.w);
+          float ysum[TBF];
+#pragma unroll
+          for (int t = 0; t < TBF; ++t) ysum[t] = 0.f;
+          const float *pp = s_partial + bd.x;
+#pragma unroll 4
+          for (int i = 0; i < nP; ++i) {             // slab band: partial sums of the slabs it touches
+            const bool on = i < bd.y;
+#pragma unroll
+            for (int t = 0; t < TBF; ++t) ysum[t] += on ? pp[t * pstride + 4 * i] : 0.f;
+          }
+          const float *dm = hmags + bd.z, *dwp = s_dw + bd.x;
+#pragma unroll 2
+          for (int i = 0; i < nD; ++i) {             // direct band: its few taps straight from the magnitudes
+            const bool on = i < bd.w;
+            const float w = on ? dwp[i] : 0.f;
+#pragma unroll
+            for (int t = 0; t < TBF; ++t) ysum[t] = fmaf(w, on ? dm[t * MS + i] : 0.f, ysum[t]);
+          }
+          if (valid) {
+            float *orow = p.out != nullptr ? p.out + (row0 + fh) * p.ld_out + j : nullptr;
+            int slot = hslot;
+#pragma unroll
+            for (int t = 0; t < TBF; ++t) {
+              const int frame = fh + t;
+              if (frame < f1) {
+                const float y = ysum[t];
+                float L = p.log_enabled ? __log10f(__fadd_rn(__fmul_rn(p.mul, y), p.add)) : y;
+                float D = 0.f;
+                if (kd > 0) {
+                  const float old = s_hist[slot * B + j];
+                  s_hist[slot * B + j] = L;
+                  if (frame >= kd) D = L - old;
+                  if (p.positive) D = fmaxf(D, 0.f);
+                  slot = (slot + 1 == kd) ? 0 : slot + 1;
+                }
+                if (p.num_classes > 0) s_lrow[t * B + j] = L;
+                if (frame >= f0) {
+                  if (orow != nullptr) {
+                    if (p.col_spec >= 0) orow[p.col_spec] = L;
+                    if (p.col_diff >= 0) orow[p.col_diff] = D;
+                  }
+                  fluxacc[t] += D;
+                }
+              }
+              if (orow != nullptr) orow += p.ld_out;
+            }
+          }
+        }
+        if (kd > 0) {                                // ring position of the next step's first frame
+          hslot += TBF;
+          while (hslot >= kd) hslot -= kd;
+        }
+        if (p.flux != nullptr || p.num_classes > 0) {
+          if (p.flux != nullptr) {
+#pragma unroll
+            for (int t = 0; t < TBF; ++t) {
+              float v = fluxacc[t];
+#pragma unroll
+              for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+              if ((tid & 31) == 0) s_red[t * 4 + (tid >> 5)] = v;
+            }
+          }
+          group_bar(g);
+          for (int t = 0; t < TBF; ++t) {
+            const int frame = fh + t;
+            if (frame < f0 || frame >= f1) continue;
+            const long long row = row0 + frame;
+            if (p.flux != nullptr && tid == 0)
+              p.flux[row] = (s_red[t * 4] + s_red[t * 4 + 1]) + (s_red[t * 4 + 2] + s_red[t * 4 + 3]);
+            if (tid < p.num_classes) {
+              float acc = 0.f;
+              for (int i = p.proj_off[tid]; i < p.proj_off[tid + 1]; ++i)
+                acc = fmaf(__ldg(&p.proj_w[i]), s_lrow[t * B + __ldg(&p.proj_band[i])], acc);
+              p.proj[row * p.ld_proj + tid] = acc;
+            }
           }
         }
       }

@@ -1,6 +1,9 @@
-// tma.cuh -- the few TMA / mbarrier primitives the front end uses (inline PTX, sm_90+ syntax, built
-// for sm_100a): one-dimensional bulk copies global -> shared that complete on an mbarrier
-// (cp.async.bulk, SASS: UBLKCP) and the matching wait.
+// tma.cuh -- asynchronous copy primitives (inline PTX, built for sm_100a).
+//   cp_async4 / cp_async_commit / cp_async_wait_all: per-thread 4-byte global -> shared copies
+//     (cp.async, SASS: LDGSTS) -- what k_front uses to stage the next step's samples: frame starts
+//     int(n*hop) - F/2 are arbitrary (hop 441 is odd), so only 4-byte copies are always aligned;
+//   tma_load_1d / mbar_*: one-dimensional bulk copies that complete on an mbarrier (cp.async.bulk,
+//     SASS: UBLKCP), usable when source and destination are 16-byte aligned.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -12,6 +15,12 @@ namespace b2 {
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+
+__device__ __forceinline__ void cp_async4(uint32_t dst_smem, const void *src_gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_smem), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t arrivals) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");

@@ -171,6 +171,10 @@ int b200spec_diff_flux_chroma(const b200spec_plan *plan, int32_t res, const floa
 /* introspection used by tests and the host layer */
 int b200spec_plan_num_res(const b200spec_plan *plan);
 int b200spec_plan_num_bands(const b200spec_plan *plan, int32_t res);
+/* how the fused kernel lays out the filterbank of one resolution: out[0] = bins per slab (odd),
+ * out[1] = slab rounds per thread, out[2] = first used bin, out[3] = one past the last used bin,
+ * out[4] = bands summed tap by tap in the band stage ("direct"), out[5] = their taps */
+int b200spec_plan_filterbank_layout(const b200spec_plan *plan, int32_t res, int32_t out[6]);
 /* number of kernel launches the library has issued in this process (bench.py's gpu_launches) */
 int64_t b200spec_launch_count(void);
 
