@@ -306,10 +306,12 @@ class FrontEnd:
 
     # ---- device-resident hot path ----------------------------------------------------------
     def run_packed(self, packed: Packed, out: Optional[torch.Tensor] = None, flux: Optional[List] = None,
-                   proj: Optional[List] = None) -> torch.Tensor:
+                   proj: Optional[List] = None, timing: Optional[List] = None) -> torch.Tensor:
         """Launch the fused kernels for every resolution; returns the stacked (rows, width) tensor.
 
         ``out=False`` skips the stacked matrix (only ``flux`` / ``proj`` are written).
+        ``timing``: a list that receives ``(resolution, start_event, end_event)`` per launch, recorded on
+        the stream the kernel runs on (read them after a synchronise).
         No synchronisation: results are ordered on the current stream.
         """
         if out is None:
@@ -336,10 +338,17 @@ class FrontEnd:
             od.d_proj = proj[r].data_ptr() if proj is not None and proj[r] is not None else None
             od.ld_proj = proj[r].shape[1] if proj is not None and proj[r] is not None else 0
             ws = self._workspace(r, packed.n_clips)
+            if timing is not None:
+                t0 = torch.cuda.Event(enable_timing=True)
+                t0.record(stream)
             _ffi.check(self._lib.b200spec_logfilt(
                 self.plan.handle, r, _ptr(packed.sig), _ptr(packed.clip_off), _ptr(packed.frame_off),
                 packed.n_clips, packed.total_frames, C.byref(od), _ptr(ws), ws.numel(),
                 C.c_void_p(stream.cuda_stream)))
+            if timing is not None:
+                t1 = torch.cuda.Event(enable_timing=True)
+                t1.record(stream)
+                timing.append((r, t0, t1))
             if use_side and r > 0:
                 self._events[r].record(stream)
                 cur.wait_event(self._events[r])

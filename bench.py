@@ -159,6 +159,34 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of each k_front kernel at the full bench size,
+    from the committed `ncu --set full` capture (profiles/; written by tools/ncu_traffic.py)."""
+    p = ROOT / "profiles" / "traffic.json"
+    try:
+        return json.loads(p.read_text())
+    except Exception:
+        return {}
+
+
+def pcie_bandwidth(dev, nbytes=1 << 30):
+    """GB/s of one large pinned H2D and D2H copy (explains the e2e bound)."""
+    import torch
+    h = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    d = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    res = {}
+    for name, (dst, src) in (("h2d_gbs", (d, h)), ("d2h_gbs", (h, d))):
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        dst.copy_(src, non_blocking=True)
+        b.record()
+        torch.cuda.synchronize(dev)
+        res[name] = nbytes / a.elapsed_time(b) / 1e6
+    return res
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -199,10 +227,11 @@ def run_ours(args, rank, world, local_rank):
         sampler.start()
     launches0 = _ffi.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launch_events = []      # (resolution, start, end) of every front-end launch inside the timed region
     barrier()
     e0.record()
     for _ in range(args.steps):
-        fe.run_packed(packed, out)
+        fe.run_packed(packed, out, timing=launch_events)
     e1.record()
     barrier()
     launches = _ffi.launch_count() - launches0
@@ -215,33 +244,25 @@ def run_ours(args, rank, world, local_rank):
     ms_per_step = elapsed_ms / args.steps
     value = world * audio_seconds / (ms_per_step * 1e-3)
 
-    # ---- dominant kernel alone (frame 4096): roofline numerator from CUDA events ------------
+    # ---- roofline of the dominant kernel: average launch duration INSIDE the timed region ----
+    # (CUDA events recorded on the launching stream around every b200spec_logfilt call; each interval
+    #  covers the one-block task-table kernel (~3 us) plus the persistent front-end kernel)
     peak, peak_src = load_peaks()
+    traffic = load_traffic()
     per_kernel = []
     for r, s in enumerate(specs):
-        fe_r = FrontEnd([s], device=local_rank, dtype="f32", channels=1)
-        out_r = fe_r.alloc_output(packed.total_frames)
-        for _ in range(2):
-            fe_r.run_packed(packed, out_r)
-        torch.cuda.synchronize(dev)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = max(2, min(args.steps, 5))
-        a.record()
-        for _ in range(reps):
-            fe_r.run_packed(packed, out_r)
-        b.record()
-        torch.cuda.synchronize(dev)
-        ms = a.elapsed_time(b) / reps
-        alg = in_bytes + out_r.numel() * 4
+        ms = float(np.mean([a.elapsed_time(b) for rr, a, b in launch_events if rr == r]))
+        alg = in_bytes + packed.total_frames * s.out_width * 4
         flops = packed.total_frames * (2.5 * s.frame_size * np.log2(s.frame_size) + s.frame_size
                                        + 4 * s.frame_size / 2 + 2 * len(s.filterbank.banded()[3]) + 3 * s.num_bands)
         per_kernel.append({"frame_size": s.frame_size, "ms": ms, "alg_bytes": alg, "gbs": alg / ms / 1e6,
-                           "fp32_tflops": flops / ms / 1e9})
-        del out_r
+                           "fp32_tflops": flops / ms / 1e9, "share_of_step": ms / ms_per_step,
+                           "traffic": traffic.get(str(s.frame_size)) if (n_clips, args.clip_seconds) == (N_CLIPS, CLIP_SECONDS) else None})
     dom = max(per_kernel, key=lambda k: k["ms"])
     fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
     roofline = {"bound": "hbm", "achieved": dom["gbs"], "peak": peak, "unit": "GB/s", "frac": dom["gbs"] / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "k_front<4096> (fused frame+FFT+filterbank+log+diff)",
+                "traffic": dom["traffic"], "traffic_source": traffic.get("source"),
+                "peak_source": peak_src, "kernel": "k_front<%d> (fused frame+FFT+filterbank+log+diff)" % dom["frame_size"],
                 "kernel_ms": dom["ms"], "alg_bytes_per_launch": dom["alg_bytes"],
                 "fp32_tflops": dom["fp32_tflops"], "fp32_frac_of_74.5": dom["fp32_tflops"] / fp32_peak,
                 "note": "hop 441 makes the path FP32-issue bound (31-78 flop/B vs ridge 11); see DESIGN.md",
@@ -276,6 +297,11 @@ def run_ours(args, rank, world, local_rank):
                "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps,
                "api": "audio_tabs_b200.plan.FrontEnd.process_batch_pinned"}
         del host_in, host_out
+        if rank == 0:
+            pc = pcie_bandwidth(dev)
+            e2e["pcie"] = pc
+            # both directions overlap: the slower copy bounds the step
+            e2e["pcie_bound_value"] = world * audio_seconds / max(in_bytes / pc["h2d_gbs"], out_bytes / pc["d2h_gbs"]) * 1e9
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
