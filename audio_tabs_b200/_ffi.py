@@ -9,7 +9,7 @@ import ctypes as C
 import os
 from pathlib import Path
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_RES = 4
 MAX_DIFF_FRAMES = 16
 
@@ -42,6 +42,7 @@ class ResDesc(C.Structure):
         ("proj_off", c_int32_p),
         ("proj_band", c_int32_p),
         ("proj_weight", c_float_p),
+        ("diff_max_bins", C.c_int32),
     ]
 
 

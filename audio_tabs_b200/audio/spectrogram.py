@@ -203,8 +203,8 @@ class SpectrogramDifference(_Stage):
                                        hop_size=spectrogram.stft.frames.hop_size, window=spectrogram.stft.window)
         if diff_frames < 1:
             raise ValueError("number of `diff_frames` must be >= 1")
-        if diff_max_bins is not None and diff_max_bins > 1:
-            raise ValueError("diff_max_bins > 1 (SuperFlux maximum filter) is not implemented on the device")
+        if diff_max_bins is not None and not 0 <= int(diff_max_bins) <= 64:
+            raise ValueError("diff_max_bins must be within [0, 64]")
         self.source = spectrogram
         self.spectrogram = spectrogram
         self.stft = spectrogram.stft

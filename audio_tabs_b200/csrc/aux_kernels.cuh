@@ -75,7 +75,7 @@ __global__ void k_filter_log(const float *__restrict__ spec, long long ld_spec, 
 
 // one warp per row: lagged (positive) difference inside each clip, flux row sum, projection
 __global__ void k_diff_flux_proj(const float *__restrict__ L, long long ld_L, const long long *__restrict__ frame_off,
-                                 int n_clips, long long rows, int B, int kd, int positive, int num_classes,
+                                 int n_clips, long long rows, int B, int kd, int positive, int max_bins, int num_classes,
                                  const int *__restrict__ proj_off, const int *__restrict__ proj_band,
                                  const float *__restrict__ proj_w, float *__restrict__ out, long long ld_out,
                                  int col_spec, int col_diff, float *__restrict__ flux, float *__restrict__ proj,
@@ -96,7 +96,19 @@ __global__ void k_diff_flux_proj(const float *__restrict__ L, long long ld_L, co
       const float v = x[j];
       float D = 0.f;
       if (kd > 0) {
-        if (local >= kd) D = v - L[(r - kd) * ld_L + j];
+        if (local >= kd) {
+          const float *ref = L + (r - kd) * ld_L;
+          float m = ref[j];
+          if (max_bins > 1) {   // scipy maximum_filter, size (1, M), origin 0, mode 'reflect': window [j - M/2, j + (M-1)/2]
+            for (int i = j - max_bins / 2; i <= j + (max_bins - 1) / 2; ++i) {
+              int q = i < 0 ? -i - 1 : i;
+              q = q >= B ? 2 * B - 1 - q : q;
+              q = min(max(q, 0), B - 1);
+              m = fmaxf(m, ref[q]);
+            }
+          }
+          D = v - m;
+        }
         if (positive) D = fmaxf(D, 0.f);
       }
       if (out != nullptr) {

@@ -62,7 +62,7 @@ struct ResPlan {
   int num_bands = 0, nnz = 0, kmax = 0;
   int log_enabled = 0;
   float mul = 1.f, add = 1.f;
-  int diff_frames = 0, positive = 0;
+  int diff_frames = 0, positive = 0, diff_max_bins = 0;
   int num_classes = 0;
   // device tables
   float *d_window = nullptr;
@@ -124,6 +124,8 @@ int build_res(b200spec_plan *pl, const b200spec_res_desc &d, ResPlan &r) {
   r.add = d.add;
   r.diff_frames = d.diff_frames;
   r.positive = d.positive_diffs;
+  if (d.diff_max_bins < 0 || d.diff_max_bins > 64) return fail(B200SPEC_ERR_UNSUPPORTED, "diff_max_bins %d outside [0, 64]", d.diff_max_bins);
+  r.diff_max_bins = d.diff_max_bins > 1 ? d.diff_max_bins : 0;
   r.num_bands = d.num_bands;
   r.num_classes = d.num_classes;
 
@@ -430,6 +432,9 @@ int b200spec_logfilt(const b200spec_plan *plan, int32_t res, const void *d_sig, 
   if (out->d_proj && r.num_classes <= 0) return fail(B200SPEC_ERR_ARG, "d_proj given but the plan has no projection");
   if (out->d_out && out->ld_out < r.num_bands) return fail(B200SPEC_ERR_ARG, "ld_out smaller than num_bands");
   if (out->col_diff >= 0 && r.diff_frames <= 0) return fail(B200SPEC_ERR_ARG, "col_diff given but diff_frames == 0");
+  if (r.diff_max_bins > 1 && (out->col_diff >= 0 || out->d_flux))
+    return fail(B200SPEC_ERR_UNSUPPORTED, "diff_max_bins > 1: the fused kernel writes the log-filtered rows only; "
+                "compute the SuperFlux difference with b200spec_diff_flux_chroma on them");
   b2::FrontParams p{};
   p.out = out->d_out;
   p.ld_out = out->ld_out;
@@ -496,7 +501,7 @@ int b200spec_diff_flux_chroma(const b200spec_plan *plan, int32_t res, const floa
   if (blocks > plan->num_sms * 8) blocks = plan->num_sms * 8;
   b2::k_diff_flux_proj<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       d_L, ld_L, reinterpret_cast<const long long *>(d_frame_off), n_clips, total_frames, B, r.diff_frames,
-      r.positive, out->d_proj ? r.num_classes : 0, r.d_proj_off, r.d_proj_band, r.d_proj_w, out->d_out,
+      r.positive, r.diff_max_bins, out->d_proj ? r.num_classes : 0, r.d_proj_off, r.d_proj_band, r.d_proj_w, out->d_out,
       out->ld_out, out->col_spec, out->col_diff, out->d_flux, out->d_proj, out->ld_proj);
   CU_CHECK(cudaGetLastError());
   g_launches++;

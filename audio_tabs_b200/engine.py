@@ -60,7 +60,7 @@ def _parse(stage):
         rec["stack"] = True
         node = node.diff
     if isinstance(node, SpectrogramDifference):
-        rec["diff"] = (node.diff_frames, bool(node.positive_diffs))
+        rec["diff"] = (node.diff_frames, bool(node.positive_diffs), int(node.diff_max_bins or 0))
         node = node.source
     if isinstance(node, LogarithmicSpectrogram):
         rec["log"] = (float(node.mul), float(node.add))
@@ -81,16 +81,16 @@ def _parse(stage):
 
 
 def _spec_from(rec, stft=None, frame_size=None):
-    diff_frames, positive = rec["diff"] if rec["diff"] else (0, False)
+    diff_frames, positive, max_bins = rec["diff"] if rec["diff"] else (0, False, 0)
     mul, add = rec["log"] if rec["log"] else (1.0, 1.0)
     fold = dict(proj_classes=rec["fold"][0], num_classes=rec["fold"][1]) if rec.get("fold") else {}
     if stft is not None:
         return ResolutionSpec(frame_size=stft.frames.frame_size, hop_size=stft.frames.hop_size,
                               origin=stft.frames.origin, fft_window=np.asarray(stft.fft_window),
                               filterbank=rec["filterbank"], log=rec["log"] is not None, mul=mul, add=add,
-                              diff_frames=diff_frames, positive_diffs=positive, **fold)
+                              diff_frames=diff_frames, positive_diffs=positive, diff_max_bins=max_bins, **fold)
     return ResolutionSpec(frame_size=frame_size, filterbank=rec["filterbank"], log=rec["log"] is not None,
-                          mul=mul, add=add, diff_frames=diff_frames, positive_diffs=positive)
+                          mul=mul, add=add, diff_frames=diff_frames, positive_diffs=positive, diff_max_bins=max_bins)
 
 
 def _frame_off(total, device):

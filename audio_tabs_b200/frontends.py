@@ -56,7 +56,7 @@ class MultiResolutionFrontEnd(Processor):
 
 def log_filt_spec(frame_size, hop_size=441.0, num_bands=12, fmin=30.0, fmax=17000.0, norm_filters=True,
                   unique_filters=True, mul=1.0, add=1.0, diff_ratio=None, positive_diffs=True,
-                  sample_rate=SAMPLE_RATE, int16=False, fold=False, origin=0):
+                  sample_rate=SAMPLE_RATE, int16=False, fold=False, origin=0, diff_max_bins=0):
     """ResolutionSpec of one madmom log-filtered-spectrogram chain (optionally with diff / chroma fold)."""
     window = np.hanning(frame_size)
     fft_window = window / 32767.0 if int16 else window
@@ -68,7 +68,7 @@ def log_filt_spec(frame_size, hop_size=441.0, num_bands=12, fmin=30.0, fmax=1700
         extra = dict(proj_classes=fold_classes(fb.center_frequencies, 12), num_classes=12)
     return ResolutionSpec(frame_size=frame_size, hop_size=hop_size, origin=origin, fft_window=fft_window,
                           filterbank=fb, log=True, mul=mul, add=add, diff_frames=k,
-                          positive_diffs=positive_diffs and k > 0, **extra)
+                          positive_diffs=positive_diffs and k > 0, diff_max_bins=diff_max_bins if k > 0 else 0, **extra)
 
 
 def beat_specs(sample_rate=SAMPLE_RATE, int16=False):

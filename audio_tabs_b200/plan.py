@@ -50,6 +50,7 @@ class ResolutionSpec:
     add: float = 1.0
     diff_frames: int = 0
     positive_diffs: bool = False
+    diff_max_bins: int = 0                      # SuperFlux maximum filter width (0 / 1 = none)
     proj_classes: Optional[np.ndarray] = None   # per band class index (or -1), e.g. chroma fold
     proj_matrix: Optional[np.ndarray] = None    # or a dense (B, C) projection
     num_classes: int = 0
@@ -94,7 +95,7 @@ class ResolutionSpec:
             self.frame_size, repr(self.hop_size), self.origin, _digest(self.window32),
             _digest(None if self.filterbank is None else np.asarray(self.filterbank)),
             int(self.log), repr(float(self.mul)), repr(float(self.add)), self.diff_frames,
-            int(self.positive_diffs), _digest(self.proj_off, self.proj_band, self.proj_weight))))
+            int(self.positive_diffs), int(self.diff_max_bins or 0), _digest(self.proj_off, self.proj_band, self.proj_weight))))
 
     @property
     def num_bins(self):
@@ -142,6 +143,7 @@ class DevicePlan:
             r.log_enabled = int(bool(s.log))
             r.mul, r.add = float(s.mul), float(s.add)
             r.diff_frames, r.positive_diffs = int(s.diff_frames), int(bool(s.positive_diffs))
+            r.diff_max_bins = int(s.diff_max_bins or 0)
             r.num_classes = int(s.num_classes) if s.proj_off is not None else 0
             if s.proj_off is not None:
                 r.proj_off, r.proj_band, r.proj_weight = iptr(s.proj_off), iptr(s.proj_band), fptr(s.proj_weight)
@@ -333,8 +335,14 @@ class FrontEnd:
             od.d_out = out.data_ptr() if out is not False else None
             od.ld_out = self.width
             od.col_spec = self.col[r]
-            od.col_diff = self.col[r] + s.num_bands if s.diff_frames > 0 else -1
-            od.d_flux = flux[r].data_ptr() if flux is not None and flux[r] is not None else None
+            superflux = s.diff_frames > 0 and (s.diff_max_bins or 0) > 1
+            want_flux = flux is not None and flux[r] is not None
+            od.col_diff = self.col[r] + s.num_bands if s.diff_frames > 0 and not superflux else -1
+            od.d_flux = flux[r].data_ptr() if want_flux and not superflux else None
+            tmp_L = None
+            if superflux and out is False:      # the SuperFlux pass needs the log-filtered rows somewhere
+                tmp_L = torch.empty((packed.total_frames, s.num_bands), dtype=torch.float32, device=self.device)
+                od.d_out, od.ld_out, od.col_spec = tmp_L.data_ptr(), s.num_bands, 0
             od.d_proj = proj[r].data_ptr() if proj is not None and proj[r] is not None else None
             od.ld_proj = proj[r].shape[1] if proj is not None and proj[r] is not None else 0
             ws = self._workspace(r, packed.n_clips)
@@ -345,6 +353,21 @@ class FrontEnd:
                 self.plan.handle, r, _ptr(packed.sig), _ptr(packed.clip_off), _ptr(packed.frame_off),
                 packed.n_clips, packed.total_frames, C.byref(od), _ptr(ws), ws.numel(),
                 C.c_void_p(stream.cuda_stream)))
+            if superflux:
+                # SuperFlux: D[n] = L[n] - maxfilter(L[n-k]) needs whole lagged rows, so it runs as a
+                # second kernel over the rows just written (they are still in L2)
+                sd = _ffi.OutDesc()
+                if tmp_L is not None:
+                    src, ld_src = tmp_L, s.num_bands
+                    sd.d_out, sd.ld_out, sd.col_spec, sd.col_diff = None, 0, -1, -1
+                else:
+                    src, ld_src = out[:, self.col[r]:], self.width
+                    sd.d_out, sd.ld_out, sd.col_spec, sd.col_diff = out.data_ptr(), self.width, -1, self.col[r] + s.num_bands
+                sd.d_flux = flux[r].data_ptr() if want_flux else None
+                sd.d_proj, sd.ld_proj = None, 0
+                _ffi.check(self._lib.b200spec_diff_flux_chroma(
+                    self.plan.handle, r, C.c_void_p(src.data_ptr()), ld_src, _ptr(packed.frame_off), packed.n_clips,
+                    packed.total_frames, C.byref(sd), C.c_void_p(stream.cuda_stream)))
             if timing is not None:
                 t1 = torch.cuda.Event(enable_timing=True)
                 t1.record(stream)

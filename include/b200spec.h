@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define B200SPEC_ABI_VERSION 1
+#define B200SPEC_ABI_VERSION 2
 #define B200SPEC_MAX_RES 4          /* resolutions per plan (RNNBeatProcessor uses 3) */
 #define B200SPEC_MAX_DIFF_FRAMES 16 /* largest supported diff lag in frames */
 
@@ -89,6 +89,12 @@ typedef struct b200spec_res_desc {
   const int32_t *proj_off;   /* host, num_classes + 1 */
   const int32_t *proj_band;  /* host, proj_off[num_classes] */
   const float *proj_weight;  /* host, proj_off[num_classes] */
+  /* SuperFlux (madmom SpectrogramDifference diff_max_bins): the lagged row is widened by a maximum
+   * filter over diff_max_bins neighbouring bands (scipy.ndimage.maximum_filter, size (1, M), 'reflect')
+   * before it is subtracted.  0 or 1 = plain difference.  With M > 1 the difference is produced by
+   * b200spec_diff_flux_chroma from the rows b200spec_logfilt wrote (col_diff / d_flux of logfilt must
+   * be unused); see FrontEnd.run_packed for the two-call sequence. */
+  int32_t diff_max_bins;
 } b200spec_res_desc;
 
 typedef struct b200spec_plan_desc {

@@ -263,3 +263,56 @@ def test_properties_at_full_clip_length(b2):
     x = sig[:n].cpu().numpy()
     want_head = ref.rnn_beat_preprocessor()(x[:SR + 4096])[:90]
     assert_close(out[:90].cpu().numpy(), want_head, what="head of 3-min stem")
+
+
+# ---- SuperFlux: SpectrogramDifference(diff_max_bins=3) -------------------------
+@pytest.mark.parametrize("max_bins,stack", [(3, True), (2, False), (5, True)])
+def test_superflux_difference(b2, max_bins, stack):
+    """madmom's SuperFlux chain: frame 2048 @ 200 fps, 24 bands/oct, log10(1+x), lagged row widened by
+    a maximum filter over `max_bins` bands (scipy.ndimage.maximum_filter, 'reflect') before subtraction."""
+    from audio_tabs_b200.synth import synth_guitar
+    x = synth_guitar(3100 + max_bins, 3.0)
+
+    def chain(m, max_bins=max_bins, stack=stack):
+        return m.SequentialProcessor((
+            m.SignalProcessor(num_channels=1, sample_rate=SR), m.FramedSignalProcessor(frame_size=2048, fps=200),
+            m.ShortTimeFourierTransformProcessor(),
+            m.FilteredSpectrogramProcessor(num_bands=24, fmin=30, fmax=17000, norm_filters=False),
+            m.LogarithmicSpectrogramProcessor(mul=1, add=1),
+            m.SpectrogramDifferenceProcessor(diff_ratio=0.5, diff_max_bins=max_bins, positive_diffs=True,
+                                             stack_diffs=np.hstack if stack else None)))
+    want = chain(ref)(x)
+    want = np.asarray(want.data if hasattr(want, "data") and not isinstance(want, np.ndarray) else want)
+    got = np.asarray(chain(b2)(x))
+    assert got.shape == want.shape and got.shape[0] == 600
+    assert_close(got, want, what="superflux M=%d" % max_bins)
+    # the maximum filter only ever lowers the positive difference
+    plain = np.asarray(chain(b2, None, False)(x))
+    sf = got[:, got.shape[1] // 2:] if stack else got
+    assert (sf <= plain + 1e-6).all() and (sf < plain - 1e-4).any()
+
+
+def test_superflux_flux_only_batch(b2):
+    """FrontEnd.run_packed with diff_max_bins > 1 and out=False: flux rows equal the row sums of the difference."""
+    import torch
+    from audio_tabs_b200.frontends import log_filt_spec
+    from audio_tabs_b200.plan import FrontEnd
+    from audio_tabs_b200.synth import synth_guitar
+    spec = log_filt_spec(2048, 441.0, 12, diff_ratio=0.5)
+    spec_sf = log_filt_spec(2048, 441.0, 12, diff_ratio=0.5, diff_max_bins=3)
+    clips = [synth_guitar(3200 + i, 1.0 + 0.37 * i) for i in range(3)]
+    fe = FrontEnd([spec_sf], device=0)
+    packed = fe.pack(clips)
+    full = fe.run_packed(packed)
+    flux = torch.empty(packed.total_frames, dtype=torch.float32, device="cuda")
+    fe.run_packed(packed, out=False, flux=[flux])
+    B = spec.num_bands
+    assert_close(flux.cpu().numpy(), full[:, B:].sum(dim=1).cpu().numpy(), rtol=1e-5, atol=1e-5, what="superflux flux")
+    o = 0
+    for c in clips:      # per clip against the oracle, rows must not leak across clip boundaries
+        t = ref.num_frames_for(len(c), 441.0)
+        L = ref.log_filtered_spectrogram(c, frame_size=2048, num_bands=12)
+        L = np.asarray(L.data if hasattr(L, "data") else L)
+        D = ref.spectrogram_difference(L, spec.diff_frames, diff_max_bins=3, positive_diffs=True)
+        assert_close(full[o:o + t, B:].cpu().numpy(), D.astype(np.float32), what="superflux batch diff")
+        o += t

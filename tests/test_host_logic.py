@@ -106,7 +106,7 @@ def test_lazy_chain_bookkeeping(lib_built):
     out = chain(x)                                   # nothing is computed yet
     assert out.shape == (100, 182) and out.dtype == np.float32
     rec = _parse(out)
-    assert rec["stack"] and rec["diff"] == (2, True) and rec["log"] == (1.0, 1.0)
+    assert rec["stack"] and rec["diff"] == (2, True, 0) and rec["log"] == (1.0, 1.0)
     assert rec["filterbank"].shape == (2048, 91) and rec["magnitude"]
     spec = _spec_from(rec, stft=rec["stft"])
     assert (spec.frame_size, spec.hop_size, spec.num_bands, spec.diff_frames, spec.out_width) == (4096, 441.0, 91, 2, 182)
