@@ -65,6 +65,7 @@ class OutDesc(C.Structure):
         ("d_flux", C.c_void_p),
         ("d_proj", C.c_void_p),
         ("ld_proj", C.c_int64),
+        ("d_clip_scale", C.c_void_p),
     ]
 
 
@@ -83,6 +84,8 @@ SYMBOLS = [
                                        C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     ("b200spec_logfilt", C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                    C.c_int64, C.POINTER(OutDesc), C.c_void_p, C.c_size_t, C.c_void_p]),
+    ("b200spec_clip_peak", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_int32,
+                                     C.c_void_p, C.c_void_p]),
     ("b200spec_magnitude", C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     ("b200spec_filter_log", C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
                                       C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),

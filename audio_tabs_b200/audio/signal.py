@@ -111,10 +111,11 @@ class SignalProcessor(Processor):
                     stop=self.stop, norm=self.norm, gain=self.gain, dtype=self.dtype)
         args.update(kwargs)
         if _is_tensor(data):
-            return DeviceSignal(data, sample_rate=args["sample_rate"], num_channels=args["num_channels"])
+            return DeviceSignal(data, sample_rate=args["sample_rate"], num_channels=args["num_channels"],
+                                norm=args["norm"])
         if isinstance(data, DeviceSignal):
             return DeviceSignal(data.data, sample_rate=data.sample_rate or args["sample_rate"],
-                                num_channels=args["num_channels"])
+                                num_channels=args["num_channels"], norm=args["norm"] or data.norm)
         src_rate = getattr(data, "sample_rate", None)
         if src_rate is not None and args["sample_rate"] is not None and src_rate != args["sample_rate"]:
             raise NotImplementedError("resampling is done by ffmpeg upstream of this path "
@@ -127,9 +128,13 @@ class SignalProcessor(Processor):
 class DeviceSignal:
     """A signal that already lives on the GPU (torch tensor); same attributes as ``Signal``."""
 
-    def __init__(self, data, sample_rate=None, num_channels=None):
+    def __init__(self, data, sample_rate=None, num_channels=None, norm=False):
         self.data = remix(data, num_channels)
         self.sample_rate = sample_rate
+        # madmom Signal(norm=True) divides by max|x|.  The samples are not rewritten: the fused chains
+        # apply 1 / max|x| (b200spec_clip_peak) as a gain on the band sums, which is the same thing
+        # because the path is linear up to the logarithm.
+        self.norm = bool(norm)
 
     def __len__(self):
         return int(self.data.shape[0])

@@ -31,6 +31,37 @@ __global__ void k_setup_tasks(const long long *__restrict__ frame_off, int n_cli
   if (t == 0) *task_counter = 0;
 }
 
+// ---- per-clip peak: max |x| of the down-mixed samples ------------------------------------------------
+// grid = (kPeakBlocksPerClip, n_clips); the clip's samples are strided over its blocks; |x| >= 0 so the
+// float bit pattern orders like an unsigned integer and atomicMax on it is exact.
+constexpr int kPeakBlocksPerClip = 32;
+template <int IN>
+__global__ void k_clip_peak(const void *__restrict__ sig, const long long *__restrict__ clip_off,
+                            unsigned int *__restrict__ peak_bits) {
+  const int c = blockIdx.y;
+  const long long s0 = clip_off[c], n = clip_off[c + 1] - s0;
+  Samples<IN> S{clip_base<IN>(sig, s0)};
+  float m = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(S.at(i)));
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+  __shared__ float s_m[32];
+  if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? s_m[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if (threadIdx.x == 0) atomicMax(peak_bits + c, __float_as_uint(m));
+  }
+}
+
+__global__ void k_peak_reciprocal(float *__restrict__ peak, int n, float eps, float numer) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) peak[i] = numer / (peak[i] + eps);
+}
+
 // ---- stand-alone stages -------------------------------------------------------------------------
 __global__ void k_magnitude(const float2 *__restrict__ in, long long n, float *__restrict__ out) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;

@@ -441,11 +441,43 @@ int b200spec_logfilt(const b200spec_plan *plan, int32_t res, const void *d_sig, 
   p.col_spec = out->col_spec;
   p.col_diff = out->col_diff;
   p.flux = out->d_flux;
+  p.clip_scale = out->d_clip_scale;
   p.proj = out->d_proj;
   p.ld_proj = out->ld_proj;
   p.num_classes = out->d_proj ? r.num_classes : 0;
   return launch_front(plan, res, b2::MODE_LOGFILT, d_sig, d_clip_off, d_frame_off, n_clips, total_frames, p,
                       d_workspace, workspace_bytes, stream);
+}
+
+int b200spec_clip_peak(const b200spec_plan *plan, const void *d_sig, const int64_t *d_clip_off, int32_t n_clips,
+                       float eps, int32_t reciprocal, float *d_peak, void *stream) {
+  if (!plan) return fail(B200SPEC_ERR_ARG, "plan is NULL");
+  if (n_clips < 0) return fail(B200SPEC_ERR_ARG, "n_clips < 0");
+  if (n_clips == 0) return 0;
+  if (!d_sig || !d_clip_off || !d_peak) return fail(B200SPEC_ERR_ARG, "NULL device pointer");
+  DeviceGuard guard;
+  CU_CHECK(guard.enter(plan->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CU_CHECK(cudaMemsetAsync(d_peak, 0, sizeof(float) * (size_t)n_clips, st));
+  const dim3 grid(b2::kPeakBlocksPerClip, (unsigned)n_clips);
+  const long long *co = reinterpret_cast<const long long *>(d_clip_off);
+  unsigned int *bits = reinterpret_cast<unsigned int *>(d_peak);
+  switch ((plan->dtype == B200SPEC_I16 ? 2 : 0) + (plan->channels == 2 ? 1 : 0)) {
+    case b2::IN_F32_MONO: b2::k_clip_peak<b2::IN_F32_MONO><<<grid, 256, 0, st>>>(d_sig, co, bits); break;
+    case b2::IN_F32_STEREO: b2::k_clip_peak<b2::IN_F32_STEREO><<<grid, 256, 0, st>>>(d_sig, co, bits); break;
+    case b2::IN_I16_MONO: b2::k_clip_peak<b2::IN_I16_MONO><<<grid, 256, 0, st>>>(d_sig, co, bits); break;
+    default: b2::k_clip_peak<b2::IN_I16_STEREO><<<grid, 256, 0, st>>>(d_sig, co, bits); break;
+  }
+  CU_CHECK(cudaGetLastError());
+  g_launches++;
+  if (reciprocal) {
+    // the int16 window is pre-divided by 32767 (madmom stft.py); the gain of a peak-normalised clip undoes it
+    const float numer = plan->dtype == B200SPEC_I16 ? 32767.f : 1.f;
+    b2::k_peak_reciprocal<<<(n_clips + 255) / 256, 256, 0, st>>>(d_peak, n_clips, eps, numer);
+    CU_CHECK(cudaGetLastError());
+    g_launches++;
+  }
+  return 0;
 }
 
 int b200spec_magnitude(const float *d_stft, int64_t n_elems, float *d_out, void *stream) {

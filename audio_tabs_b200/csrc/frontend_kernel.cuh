@@ -65,6 +65,7 @@ struct FrontParams {
   long long ld_out;
   int col_spec, col_diff;
   float *flux;
+  const float *clip_scale;   // per-clip gain on the band sums (nullptr = 1)
   float *proj;
   long long ld_proj;
   // outputs (MODE_SPECTRUM)
@@ -243,6 +244,7 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
     const int f1 = min(T, f0 + p.chunk);
     const int fs = (MODE == MODE_LOGFILT && kd > 0) ? max(0, f0 - kd) : f0;  // warm-up rows for the diff
     Samples<IN> S{clip_base<IN>(p.sig, samp0)};
+    const float cscale = (MODE == MODE_LOGFILT && p.clip_scale != nullptr) ? __ldg(p.clip_scale + c) : 1.f;
 
     int hslot = (MODE == MODE_LOGFILT && kd > 0) ? fs % kd : 0;   // difference ring slot of frame f
     for (int fb = fs; fb < f1; fb += TB) {
@@ -386,7 +388,7 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
             for (int t = 0; t < TBF; ++t) {
               const int frame = fh + t;
               if (frame < f1) {
-                const float y = ysum[t];
+                const float y = ysum[t] * cscale;
                 float L = p.log_enabled ? __log10f(__fadd_rn(__fmul_rn(p.mul, y), p.add)) : y;
                 float D = 0.f;
                 if (kd > 0) {

@@ -145,18 +145,23 @@ def run_chain(stage, kind=None):
     spec = _spec_from(rec, stft=stft)
     packed = Packed(sig, [sig.shape[0]], spec.hop_size, num_frames=[frames.num_frames])
 
+    norm = bool(getattr(frames.signal, "norm", False)) and not isinstance(frames.signal, np.ndarray)
     if rec["filterbank"] is not None:
         fe = FrontEnd([spec], device=device.index, dtype=dtype, channels=1)
         B = spec.num_bands
+        scale = fe.peak_scales(packed, eps=0.0) if norm else None     # device signal with norm=True
         if rec["fold"] is not None:
             proj = torch.empty((packed.total_frames, spec.num_classes), dtype=torch.float32, device=device)
-            fe.run_packed(packed, out=False, proj=[proj])
+            fe.run_packed(packed, out=False, proj=[proj], clip_scale=scale)
             return proj
         if rec["diff"] is None or rec["stack"]:
-            return fe.run_packed(packed)                     # [spec] or [spec | diff]
-        full = fe.run_packed(packed)                         # diff only: second half of the stacked rows
+            return fe.run_packed(packed, clip_scale=scale)   # [spec] or [spec | diff]
+        full = fe.run_packed(packed, clip_scale=scale)       # diff only: second half of the stacked rows
         return full[:, B:].contiguous()
 
+    if norm:
+        raise ValueError("norm=True on a device-resident signal is applied as a gain inside the fused "
+                         "filterbank chains; normalise the tensor yourself for a bare STFT / spectrogram")
     fe = FrontEnd([spec], device=device.index, dtype=dtype, channels=1)
     if not rec["magnitude"]:
         return fe.stft_packed(packed, 0, complex_out=True)

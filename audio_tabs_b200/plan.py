@@ -308,11 +308,13 @@ class FrontEnd:
 
     # ---- device-resident hot path ----------------------------------------------------------
     def run_packed(self, packed: Packed, out: Optional[torch.Tensor] = None, flux: Optional[List] = None,
-                   proj: Optional[List] = None, timing: Optional[List] = None) -> torch.Tensor:
+                   proj: Optional[List] = None, timing: Optional[List] = None,
+                   clip_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Launch the fused kernels for every resolution; returns the stacked (rows, width) tensor.
 
         ``out=False`` skips the stacked matrix (only ``flux`` / ``proj`` are written).
-        ``timing``: a list that receives ``(resolution, start_event, end_event)`` per launch, recorded on
+        ``clip_scale``: (n_clips,) float32 device tensor of per-clip gains applied before the logarithm
+        (see :meth:`peak_scales`); ``timing``: a list that receives ``(resolution, start_event, end_event)`` per launch, recorded on
         the stream the kernel runs on (read them after a synchronise).
         No synchronisation: results are ordered on the current stream.
         """
@@ -345,6 +347,7 @@ class FrontEnd:
                 od.d_out, od.ld_out, od.col_spec = tmp_L.data_ptr(), s.num_bands, 0
             od.d_proj = proj[r].data_ptr() if proj is not None and proj[r] is not None else None
             od.ld_proj = proj[r].shape[1] if proj is not None and proj[r] is not None else 0
+            od.d_clip_scale = clip_scale.data_ptr() if clip_scale is not None else None
             ws = self._workspace(r, packed.n_clips)
             if timing is not None:
                 t0 = torch.cuda.Event(enable_timing=True)
@@ -375,6 +378,17 @@ class FrontEnd:
             if use_side and r > 0:
                 self._events[r].record(stream)
                 cur.wait_event(self._events[r])
+        return out
+
+    def peak_scales(self, packed: Packed, eps: float = 1e-9, reciprocal: bool = True) -> torch.Tensor:
+        """Per-clip ``1 / (max|x| + eps)`` (or the peak itself) computed on the device in one read of the
+        samples: the gain that makes ``run_packed(..., clip_scale=...)`` return the spectrogram of the
+        peak-normalised clip (/root/reference/backend/app/services/audio.py:24-26; madmom ``norm=True``
+        is ``eps=0``)."""
+        out = torch.empty(packed.n_clips, dtype=torch.float32, device=self.device)
+        _ffi.check(self._lib.b200spec_clip_peak(self.plan.handle, _ptr(packed.sig), _ptr(packed.clip_off),
+                                                packed.n_clips, float(eps), int(bool(reciprocal)), _ptr(out),
+                                                _stream_ptr(None, self.device)))
         return out
 
     def stft_packed(self, packed: Packed, res: int = 0, complex_out: bool = True) -> torch.Tensor:
@@ -465,10 +479,15 @@ class FrontEnd:
         return host_out
 
     # ---- host in / host out ----------------------------------------------------------------
-    def process_batch(self, signals: Sequence, return_tensors: bool = False):
-        """signals: list of host arrays (float32 / int16; (N,) or (N, 2)). Returns one (T_i, width) per clip."""
+    def process_batch(self, signals: Sequence, return_tensors: bool = False, peak_normalize: bool = False,
+                      eps: float = 1e-9):
+        """signals: list of host arrays (float32 / int16; (N,) or (N, 2)). Returns one (T_i, width) per clip.
+
+        ``peak_normalize``: each clip is treated as ``y / (max|y| + eps)`` -- what the reference does before
+        this path (/root/reference/backend/app/services/audio.py:24-26) -- fused as a per-clip gain."""
         packed = self.pack(signals)
-        out = self.run_packed(packed)
+        scale = self.peak_scales(packed, eps=eps) if peak_normalize else None
+        out = self.run_packed(packed, clip_scale=scale)
         if return_tensors:
             return [out[packed.frame_off_host[i]:packed.frame_off_host[i + 1]] for i in range(packed.n_clips)]
         host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)

@@ -116,6 +116,11 @@ typedef struct b200spec_out_desc {
   float *d_flux;     /* (total_frames,) row sums of the difference (spectral flux), or NULL */
   float *d_proj;     /* (total_frames, ld_proj) projection output, or NULL */
   int64_t ld_proj;
+  /* optional per-clip gain applied to the band sums before the logarithm (n_clips floats, device).
+   * The path is linear up to there, so scale[c] = 1 / (max|x_c| + 1e-9) from b200spec_clip_peak gives
+   * the spectrogram of the peak-normalised clip (services/audio.py:24-26 peak_normalize; madmom
+   * Signal(norm=True)) without a pass that rewrites the samples.  NULL = no gain. */
+  const float *d_clip_scale;
 } b200spec_out_desc;
 
 int b200spec_abi_version(void);
@@ -158,6 +163,17 @@ int b200spec_spectrogram(const b200spec_plan *plan, int32_t res, const void *d_s
 int b200spec_logfilt(const b200spec_plan *plan, int32_t res, const void *d_sig, const int64_t *d_clip_off,
                      const int64_t *d_frame_off, int32_t n_clips, int64_t total_frames,
                      const b200spec_out_desc *out, void *d_workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * Per-clip peak of the (down-mixed) samples: d_peak[c] = max_n |x_c[n]| in the plan's sample format
+ * (float32 units, or int16 units for B200SPEC_I16; stereo is down-mixed first exactly as the front end
+ * does).  With reciprocal != 0 the result is 1 / (peak + eps) instead (32767 / (peak + eps) for
+ * B200SPEC_I16, whose window is pre-divided by 32767), ready to be passed as
+ * b200spec_out_desc.d_clip_scale.  Replaces peak_normalize (/root/reference/backend/app/services/audio.py:24-26)
+ * and madmom Signal(norm=True) (eps = 0).  One read of the samples, no write.
+ */
+int b200spec_clip_peak(const b200spec_plan *plan, const void *d_sig, const int64_t *d_clip_off, int32_t n_clips,
+                       float eps, int32_t reciprocal, float *d_peak, void *stream);
 
 /*
  * Stand-alone stages on caller-supplied matrices (used when a madmom chain is not fusable,

@@ -316,3 +316,60 @@ def test_superflux_flux_only_batch(b2):
         D = ref.spectrogram_difference(L, spec.diff_frames, diff_max_bins=3, positive_diffs=True)
         assert_close(full[o:o + t, B:].cpu().numpy(), D.astype(np.float32), what="superflux batch diff")
         o += t
+
+
+# ---- ingest: per-clip peak + fused peak normalisation ---------------------------
+@pytest.mark.parametrize("dtype,channels", [("f32", 1), ("f32", 2), ("i16", 1), ("i16", 2)])
+def test_clip_peak_and_fused_normalisation(b2, dtype, channels):
+    """b200spec_clip_peak + d_clip_scale == the front end of the peak-normalised clip
+    (services/audio.py:24-26 peak_normalize for float input; madmom Signal(norm=True) with eps = 0)."""
+    import torch
+    from audio_tabs_b200.frontends import beat_specs
+    from audio_tabs_b200.plan import FrontEnd
+    from audio_tabs_b200.synth import synth_guitar
+    rng = np.random.default_rng(77)
+    clips = []
+    for i in range(3):
+        y = synth_guitar(3300 + i, 0.8 + 0.5 * i) * (0.05 + 0.3 * i)      # different peaks per clip
+        if channels == 2:
+            y = np.stack([y, np.roll(y, 7) * 0.5 + rng.standard_normal(len(y)).astype(np.float32) * 0.01], axis=1)
+        if dtype == "i16":
+            y = np.clip(np.round(y * 20000), -32768, 32767).astype(np.int16)
+        clips.append(np.ascontiguousarray(y))
+    fe = FrontEnd(beat_specs(int16=(dtype == "i16")), device=0, dtype=dtype, channels=channels)
+    packed = fe.pack(clips)
+    eps = 1e-9 if dtype == "f32" else 0.0
+    peaks = fe.peak_scales(packed, reciprocal=False).cpu().numpy()
+    mono = [ref.remix(c, 1) if channels == 2 else c for c in clips]
+    assert np.array_equal(peaks, np.array([np.abs(m.astype(np.float32)).max() for m in mono], np.float32))
+    got = fe.run_packed(packed, clip_scale=fe.peak_scales(packed, eps=eps)).cpu().numpy()
+    o = 0
+    for m in mono:
+        x = m.astype(np.float32)
+        x = x / (np.abs(x).max() + np.float32(eps))
+        want = ref.rnn_beat_preprocessor()(x)
+        assert_close(got[o:o + len(want)], want, what="normalised %s/%d" % (dtype, channels))
+        o += len(want)
+    assert o == got.shape[0]
+
+
+def test_device_signal_norm_through_processors(b2):
+    """SignalProcessor(norm=True) on a CUDA tensor: same result as madmom's host-side normalisation."""
+    import torch
+    from audio_tabs_b200.synth import synth_guitar
+    x = synth_guitar(3400, 2.0) * 0.23
+
+    def chain(m):
+        return m.SequentialProcessor((
+            m.SignalProcessor(num_channels=1, sample_rate=SR, norm=True), m.FramedSignalProcessor(frame_size=2048, fps=100),
+            m.ShortTimeFourierTransformProcessor(), m.LogarithmicFilteredSpectrogramProcessor(num_bands=12)))
+    want = chain(ref)(x).data
+    got_dev = np.asarray(chain(b2)(torch.from_numpy(x).cuda()))
+    got_host = np.asarray(chain(b2)(x))
+    assert_close(got_dev, want, what="norm on device tensor")
+    assert_close(got_host, want, what="norm on host array")
+    from audio_tabs_b200.frontends import log_filt_spec
+    from audio_tabs_b200.plan import FrontEnd
+    outs = FrontEnd([log_filt_spec(2048, 441.0, 12)], device=0).process_batch([x, x * 3.0], peak_normalize=True, eps=0.0)
+    assert_close(outs[0], want, what="process_batch peak_normalize")
+    assert_close(outs[1], want, what="process_batch peak_normalize (gain invariance)")
