@@ -5,7 +5,7 @@ Public surface mirrors madmom's processors for this path; the compute lives in l
 """
 from .processors import ParallelProcessor, Processor, SequentialProcessor  # noqa: F401
 from .filters import (Filterbank, LogarithmicFilterbank, PitchClassProfileFilterbank,  # noqa: F401
-                      TriangularFilter)
+                      SlaneyMelFilterbank, TriangularFilter)
 from .audio.signal import FramedSignal, FramedSignalProcessor, Signal, SignalProcessor  # noqa: F401
 from .audio.stft import ShortTimeFourierTransform, ShortTimeFourierTransformProcessor  # noqa: F401
 from .audio.spectrogram import (FilteredSpectrogram, FilteredSpectrogramProcessor,  # noqa: F401

@@ -43,6 +43,9 @@ class ResDesc(C.Structure):
         ("proj_band", c_int32_p),
         ("proj_weight", c_float_p),
         ("diff_max_bins", C.c_int32),
+        ("power", C.c_int32),
+        ("log_scale", C.c_float),
+        ("log_floor", C.c_float),
     ]
 
 
@@ -86,6 +89,9 @@ SYMBOLS = [
                                    C.c_int64, C.POINTER(OutDesc), C.c_void_p, C.c_size_t, C.c_void_p]),
     ("b200spec_clip_peak", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_int32,
                                      C.c_void_p, C.c_void_p]),
+    ("b200spec_onset_envelope", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int64,
+                                          C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                          C.c_void_p]),
     ("b200spec_magnitude", C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     ("b200spec_filter_log", C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
                                       C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),

@@ -62,6 +62,88 @@ __global__ void k_peak_reciprocal(float *__restrict__ peak, int n, float eps, fl
   if (i < n) peak[i] = numer / (peak[i] + eps);
 }
 
+// ---- onset-strength envelope (librosa.onset.onset_strength on rows of a (T, B) matrix) ------------------
+// one block per clip: maximum of the clip's rows (power_to_db's top_db clip is relative to it)
+__global__ void k_clip_rowmax(const float *__restrict__ L, long long ld_L, int B, const long long *__restrict__ frame_off,
+                              float *__restrict__ clip_max) {
+  const int c = blockIdx.x;
+  const long long r0 = frame_off[c], rows = frame_off[c + 1] - r0;
+  float m = -INFINITY;
+  for (long long i = threadIdx.x; i < rows * B; i += blockDim.x) m = fmaxf(m, L[(r0 + i / B) * ld_L + i % B]);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+  __shared__ float s_m[32];
+  if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? s_m[threadIdx.x] : -INFINITY;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if (threadIdx.x == 0) clip_max[c] = m;
+  }
+}
+
+// one warp per output row; dynamic shared memory: B floats per warp (the row of positive differences)
+__global__ void k_onset_env(const float *__restrict__ L, long long ld_L, int B, const long long *__restrict__ frame_off,
+                            int n_clips, long long rows, int lag, float top_db, int aggregate, int shift,
+                            const float *__restrict__ clip_max, float *__restrict__ env) {
+  extern __shared__ float s_rows[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float *row = s_rows + (size_t)wib * B;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < rows; r += nwarps) {
+    int lo = 0, hi = n_clips;
+    while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (frame_off[mid] <= r) lo = mid; else hi = mid;
+    }
+    const long long t = r - frame_off[lo];          // output index inside the clip
+    const long long src = t - shift;                // row whose difference lands here
+    if (src < lag) {                                // leading zeros: lag + centre shift (np.pad)
+      if (lane == 0) env[r] = 0.f;
+      continue;
+    }
+    const float floor_db = top_db >= 0.f ? clip_max[lo] - top_db : -INFINITY;
+    const float *a = L + (r - shift) * ld_L, *b = a - (long long)lag * ld_L;
+    float sum = 0.f;
+    for (int j = lane; j < B; j += 32) {
+      const float d = fmaxf(0.f, fmaxf(a[j], floor_db) - fmaxf(b[j], floor_db));
+      row[j] = d;
+      sum += d;
+    }
+    float result;
+    if (aggregate == 0) {
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+      result = sum / (float)B;
+    } else {
+      __syncwarp();
+      // rank of every element (ties broken by index); the two middle order statistics give np.median
+      const int k_hi = B >> 1, k_lo = (B & 1) ? k_hi : k_hi - 1;
+      float v_lo = 0.f, v_hi = 0.f;
+      for (int j = lane; j < B; j += 32) {
+        const float v = row[j];
+        int rank = 0;
+        for (int i = 0; i < B; ++i) {
+          const float w = row[i];
+          rank += (w < v) || (w == v && i < j);
+        }
+        if (rank == k_lo) v_lo = v;
+        if (rank == k_hi) v_hi = v;
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {            // exactly one lane holds each of them; the rest hold 0 (values are >= 0)
+        v_lo = fmaxf(v_lo, __shfl_xor_sync(0xffffffffu, v_lo, d));
+        v_hi = fmaxf(v_hi, __shfl_xor_sync(0xffffffffu, v_hi, d));
+      }
+      result = (v_lo + v_hi) * 0.5f;
+      __syncwarp();
+    }
+    if (lane == 0) env[r] = result;
+  }
+}
+
 // ---- stand-alone stages -------------------------------------------------------------------------
 __global__ void k_magnitude(const float2 *__restrict__ in, long long n, float *__restrict__ out) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
@@ -75,8 +157,8 @@ __global__ void k_magnitude(const float2 *__restrict__ in, long long n, float *_
 __global__ void k_filter_log(const float *__restrict__ spec, long long ld_spec, long long rows, int num_bins,
                              int num_bands, const int *__restrict__ band_start, const int *__restrict__ band_len,
                              const int *__restrict__ band_woff, const float *__restrict__ weights,
-                             int apply_filter, int apply_log, float mul, float add,
-                             float *__restrict__ out, long long ld_out) {
+                             int apply_filter, int apply_log, float mul, float add, int power, float log_scale,
+                             float log_floor, float *__restrict__ out, long long ld_out) {
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -86,18 +168,31 @@ __global__ void k_filter_log(const float *__restrict__ spec, long long ld_spec, 
       for (int j = 0; j < num_bands; ++j) {
         const int st = band_start[j], len = band_len[j], wo = band_woff[j];
         float acc = 0.f;
-        for (int i = lane; i < len; i += 32) acc = fmaf(weights[wo + i], x[st + i], acc);
+        for (int i = lane; i < len; i += 32) {
+          float m = x[st + i];
+          if (power) m *= m;
+          acc = fmaf(weights[wo + i], m, acc);
+        }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
         if (lane == 0) {
-          if (apply_log) acc = log10f(__fadd_rn(__fmul_rn(mul, acc), add));
+          if (apply_log) {
+            float a = __fadd_rn(__fmul_rn(mul, acc), add);
+            if (log_floor > 0.f) a = fmaxf(a, log_floor);
+            acc = log10f(a) * log_scale;
+          }
           out[r * ld_out + j] = acc;
         }
       }
     } else {
       for (int j = lane; j < num_bins; j += 32) {
         float y = x[j];
-        if (apply_log) y = log10f(__fadd_rn(__fmul_rn(mul, y), add));
+        if (power) y *= y;
+        if (apply_log) {
+          float a = __fadd_rn(__fmul_rn(mul, y), add);
+          if (log_floor > 0.f) a = fmaxf(a, log_floor);
+          y = log10f(a) * log_scale;
+        }
         out[r * ld_out + j] = y;
       }
     }

@@ -62,6 +62,8 @@ struct ResPlan {
   int num_bands = 0, nnz = 0, kmax = 0;
   int log_enabled = 0;
   float mul = 1.f, add = 1.f;
+  int power = 0;
+  float log_scale = 1.f, log_floor = 0.f;
   int diff_frames = 0, positive = 0, diff_max_bins = 0;
   int num_classes = 0;
   // device tables
@@ -122,6 +124,9 @@ int build_res(b200spec_plan *pl, const b200spec_res_desc &d, ResPlan &r) {
   r.log_enabled = d.log_enabled;
   r.mul = d.mul;
   r.add = d.add;
+  r.power = d.power != 0;
+  r.log_scale = d.log_scale == 0.f ? 1.f : d.log_scale;   // a zeroed descriptor means madmom's plain log10
+  r.log_floor = d.log_floor;
   r.diff_frames = d.diff_frames;
   r.positive = d.positive_diffs;
   if (d.diff_max_bins < 0 || d.diff_max_bins > 64) return fail(B200SPEC_ERR_UNSUPPORTED, "diff_max_bins %d outside [0, 64]", d.diff_max_bins);
@@ -302,6 +307,9 @@ int launch_front(const b200spec_plan *pl, int res, int mode, const void *d_sig, 
   p.log_enabled = r.log_enabled;
   p.mul = r.mul;
   p.add = r.add;
+  p.power = r.power;
+  p.log_scale = r.log_scale;
+  p.log_floor = r.log_floor;
   p.diff_frames = r.diff_frames;
   p.positive = r.positive;
   p.proj_off = r.d_proj_off;
@@ -480,6 +488,30 @@ int b200spec_clip_peak(const b200spec_plan *plan, const void *d_sig, const int64
   return 0;
 }
 
+int b200spec_onset_envelope(const float *d_L, int64_t ld_L, int32_t num_bands, const int64_t *d_frame_off,
+                            int32_t n_clips, int64_t total_frames, int32_t lag, float top_db, int32_t aggregate,
+                            int32_t shift, float *d_clip_max, float *d_env, void *stream) {
+  if (n_clips < 0 || total_frames < 0) return fail(B200SPEC_ERR_ARG, "negative sizes");
+  if (n_clips == 0 || total_frames == 0) return 0;
+  if (!d_L || !d_frame_off || !d_clip_max || !d_env) return fail(B200SPEC_ERR_ARG, "NULL device pointer");
+  if (num_bands < 1 || num_bands > 1024 || ld_L < num_bands) return fail(B200SPEC_ERR_ARG, "num_bands outside [1, 1024] or ld_L < num_bands");
+  if (lag < 1 || shift < 0) return fail(B200SPEC_ERR_ARG, "lag must be >= 1 and shift >= 0");
+  if (aggregate != 0 && aggregate != 1) return fail(B200SPEC_ERR_ARG, "aggregate must be 0 (mean) or 1 (median)");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long *fo = reinterpret_cast<const long long *>(d_frame_off);
+  b2::k_clip_rowmax<<<n_clips, 1024, 0, st>>>(d_L, ld_L, num_bands, fo, d_clip_max);
+  CU_CHECK(cudaGetLastError());
+  g_launches++;
+  long long blocks = (total_frames + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  const size_t smem = sizeof(float) * 8 * (size_t)num_bands;
+  b2::k_onset_env<<<(int)blocks, 256, smem, st>>>(d_L, ld_L, num_bands, fo, n_clips, total_frames, lag, top_db,
+                                                  aggregate, shift, d_clip_max, d_env);
+  CU_CHECK(cudaGetLastError());
+  g_launches++;
+  return 0;
+}
+
 int b200spec_magnitude(const float *d_stft, int64_t n_elems, float *d_out, void *stream) {
   if (n_elems < 0) return fail(B200SPEC_ERR_ARG, "n_elems < 0");
   if (n_elems == 0) return 0;
@@ -510,7 +542,7 @@ int b200spec_filter_log(const b200spec_plan *plan, int32_t res, const float *d_s
   const int num_bins = apply_filter ? r.frame_size / 2 : (int)ld_spec;
   b2::k_filter_log<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       d_spec, ld_spec, total_frames, num_bins, r.num_bands, r.d_band_start, r.d_band_len, r.d_band_woff, r.d_fbw,
-      apply_filter, apply_log, r.mul, r.add, d_out, ld_out);
+      apply_filter, apply_log, r.mul, r.add, r.power, r.log_scale, r.log_floor, d_out, ld_out);
   CU_CHECK(cudaGetLastError());
   g_launches++;
   return 0;

@@ -29,7 +29,8 @@ namespace b2 {
 // descriptors, no data-dependent control flow.  s_part[t * pstride + 4 * slab + r] receives the sum
 // for the band with index r modulo 4.
 // W4G: the weight table did not fit in shared memory and is read from global memory (read-only path).
-template <int L, int TBF, int MS, bool W4G = false>
+// POW: the filterbank works on the power spectrum: every magnitude is squared as it is read.
+template <int L, int TBF, int MS, bool W4G = false, bool POW = false>
 B2_HD void fb_slabs(const float4 *s_w4, const float *s_mags, float *s_part, int ns, int kmin, int pstride, int tid) {
   for (int s = 0; s < ns; ++s) {
     const int g = s * kGroupThreads + tid;
@@ -49,7 +50,8 @@ B2_HD void fb_slabs(const float4 *s_w4, const float *s_mags, float *s_part, int 
 #endif
 #pragma unroll
       for (int t = 0; t < TBF; ++t) {
-        const float m = mp[t * MS + i];
+        float m = mp[t * MS + i];
+        if (POW) m *= m;
         acc[t].x = fmaf(w.x, m, acc[t].x);
         acc[t].y = fmaf(w.y, m, acc[t].y);
         acc[t].z = fmaf(w.z, m, acc[t].z);
@@ -61,17 +63,17 @@ B2_HD void fb_slabs(const float4 *s_w4, const float *s_mags, float *s_part, int 
   }
 }
 
-template <int TBF, int MS>
+template <int TBF, int MS, bool POW = false>
 B2_HD void fb_slabs_dispatch(int L, const float4 *s_w4, const float *s_mags, float *s_part, int ns, int kmin,
                              int pstride, int tid) {
   switch (L) {
-    case 3: fb_slabs<3, TBF, MS>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
-    case 5: fb_slabs<5, TBF, MS>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
-    case 7: fb_slabs<7, TBF, MS>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
-    case 9: fb_slabs<9, TBF, MS>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
-    case 11: fb_slabs<11, TBF, MS>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
-    case 13: fb_slabs<13, TBF, MS>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
-    default: fb_slabs<15, TBF, MS>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
+    case 3: fb_slabs<3, TBF, MS, false, POW>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
+    case 5: fb_slabs<5, TBF, MS, false, POW>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
+    case 7: fb_slabs<7, TBF, MS, false, POW>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
+    case 9: fb_slabs<9, TBF, MS, false, POW>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
+    case 11: fb_slabs<11, TBF, MS, false, POW>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
+    case 13: fb_slabs<13, TBF, MS, false, POW>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
+    default: fb_slabs<15, TBF, MS, false, POW>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
   }
 }
 

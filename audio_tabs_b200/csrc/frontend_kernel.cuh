@@ -56,6 +56,8 @@ struct FrontParams {
   const float *fb_dw;    // weights of the direct bands
   int log_enabled;
   float mul, add;
+  int power;               // 1: filterbank on |X|^2 (the magnitudes are squared as they are read)
+  float log_scale, log_floor;
   int diff_frames, positive;
   int num_classes;
   const int *proj_off, *proj_band;
@@ -349,8 +351,14 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
         if (h > 0) group_bar(g);                     // the previous sub-batch is done with s_partial
         const float *hmags = s_mags + h * MS;
         // ---- K2a: slab filterbank ----
-        if (p.fb_w4_global) fb_slabs<15, TBF, MS, true>(p.fb_w4, hmags, s_partial, p.fb_ns, p.fb_kmin, pstride, tid);
-        else fb_slabs_dispatch<TBF, MS>(p.fb_L, s_w4, hmags, s_partial, p.fb_ns, p.fb_kmin, pstride, tid);
+        if (p.fb_w4_global) {
+          if (p.power) fb_slabs<15, TBF, MS, true, true>(p.fb_w4, hmags, s_partial, p.fb_ns, p.fb_kmin, pstride, tid);
+          else fb_slabs<15, TBF, MS, true, false>(p.fb_w4, hmags, s_partial, p.fb_ns, p.fb_kmin, pstride, tid);
+        } else if (p.power) {
+          fb_slabs_dispatch<TBF, MS, true>(p.fb_L, s_w4, hmags, s_partial, p.fb_ns, p.fb_kmin, pstride, tid);
+        } else {
+          fb_slabs_dispatch<TBF, MS, false>(p.fb_L, s_w4, hmags, s_partial, p.fb_ns, p.fb_kmin, pstride, tid);
+        }
         group_bar(g);
         // ---- K2b/K3: band sum, log10, lagged difference, stacked store ----
         // lane = band.  Trip counts are made warp-uniform (REDUX max) and lanes past their own count
@@ -379,7 +387,11 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
             const bool on = i < bd.w;
             const float w = on ? dwp[i] : 0.f;
 #pragma unroll
-            for (int t = 0; t < TBF; ++t) ysum[t] = fmaf(w, on ? dm[t * MS + i] : 0.f, ysum[t]);
+            for (int t = 0; t < TBF; ++t) {
+              float m = on ? dm[t * MS + i] : 0.f;
+              if (p.power) m *= m;
+              ysum[t] = fmaf(w, m, ysum[t]);
+            }
           }
           if (valid) {
             float *orow = p.out != nullptr ? p.out + (row0 + fh) * p.ld_out + j : nullptr;
@@ -389,7 +401,12 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
               const int frame = fh + t;
               if (frame < f1) {
                 const float y = ysum[t] * cscale;
-                float L = p.log_enabled ? __log10f(__fadd_rn(__fmul_rn(p.mul, y), p.add)) : y;
+                float L = y;
+                if (p.log_enabled) {
+                  float a = __fadd_rn(__fmul_rn(p.mul, y), p.add);
+                  if (p.log_floor > 0.f) a = fmaxf(a, p.log_floor);
+                  L = __log10f(a) * p.log_scale;
+                }
                 float D = 0.f;
                 if (kd > 0) {
                   const float old = s_hist[slot * B + j];

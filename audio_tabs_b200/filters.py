@@ -259,3 +259,70 @@ def fold_classes(center_frequencies, num_classes=12):
     """Pitch class (0 = C) of each band centre, as madmom.audio.chroma.CLPChroma folds bands."""
     midi = np.round(hz2midi(center_frequencies)).astype(int)
     return np.mod(midi, num_classes)
+
+
+# ---- librosa-style mel filterbank (onset strength; SURVEY.md §8f N3) -------------------------------------
+def _hz_to_mel(f):
+    """librosa.hz_to_mel (Slaney scale: linear below 1 kHz, logarithmic above)."""
+    f = np.asanyarray(f, dtype=float)
+    f_sp = 200.0 / 3
+    mels = f / f_sp
+    min_log_hz, logstep = 1000.0, np.log(6.4) / 27.0
+    min_log_mel = min_log_hz / f_sp
+    if f.ndim:
+        log_t = f >= min_log_hz
+        mels[log_t] = min_log_mel + np.log(f[log_t] / min_log_hz) / logstep
+    elif f >= min_log_hz:
+        mels = min_log_mel + np.log(f / min_log_hz) / logstep
+    return mels
+
+
+def _mel_to_hz(mels):
+    """librosa.mel_to_hz (Slaney scale)."""
+    mels = np.asanyarray(mels, dtype=float)
+    f_sp = 200.0 / 3
+    freqs = f_sp * mels
+    min_log_hz, logstep = 1000.0, np.log(6.4) / 27.0
+    min_log_mel = min_log_hz / f_sp
+    if mels.ndim:
+        log_t = mels >= min_log_mel
+        freqs[log_t] = min_log_hz * np.exp(logstep * (mels[log_t] - min_log_mel))
+    elif mels >= min_log_mel:
+        freqs = min_log_hz * np.exp(logstep * (mels - min_log_mel))
+    return freqs
+
+
+class SlaneyMelFilterbank(Filterbank):
+    """``librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax, htk=False, norm='slaney')`` as a Filterbank.
+
+    librosa 0.10.2 (pinned at /root/reference/backend/requirements.txt:14) builds ``(n_mels, 1 + n_fft/2)``
+    float32 weights; the reference reaches them through ``librosa.onset.onset_strength``
+    (services/accompaniment/strum.py:114, services/analysis/content_classifier.py:48,92).  This class is
+    the transpose without the Nyquist row: the FFT kernels produce bins ``0 .. n_fft/2 - 1``, and with the
+    default ``fmax = sr/2`` the last triangle reaches zero exactly at the Nyquist bin (its weight there is
+    ~1e-17 from rounding), so nothing measurable is dropped.  A smaller ``fmax`` is exact.
+    """
+
+    def __new__(cls, sample_rate, n_fft, n_mels=128, fmin=0.0, fmax=None):
+        if fmax is None:
+            fmax = float(sample_rate) / 2
+        fftfreqs = np.fft.rfftfreq(n=int(n_fft), d=1.0 / sample_rate)
+        mel_f = _mel_to_hz(np.linspace(_hz_to_mel(fmin), _hz_to_mel(fmax), int(n_mels) + 2))
+        fdiff = np.diff(mel_f)
+        ramps = np.subtract.outer(mel_f, fftfreqs)
+        weights = np.zeros((int(n_mels), len(fftfreqs)), dtype=FILTER_DTYPE)
+        for i in range(int(n_mels)):
+            lower = -ramps[i] / fdiff[i]
+            upper = ramps[i + 2] / fdiff[i + 1]
+            weights[i] = np.maximum(0, np.minimum(lower, upper))
+        enorm = 2.0 / (mel_f[2:int(n_mels) + 2] - mel_f[:int(n_mels)])
+        weights *= enorm[:, np.newaxis]
+        obj = Filterbank.__new__(cls, np.ascontiguousarray(weights[:, :-1].T), fftfreqs[:-1])
+        obj.mel_frequencies = mel_f
+        return obj
+
+    def __array_finalize__(self, obj):
+        Filterbank.__array_finalize__(self, obj)
+        if obj is None:
+            return
+        self.mel_frequencies = getattr(obj, "mel_frequencies", None)

@@ -51,6 +51,9 @@ class ResolutionSpec:
     diff_frames: int = 0
     positive_diffs: bool = False
     diff_max_bins: int = 0                      # SuperFlux maximum filter width (0 / 1 = none)
+    power: bool = False                         # filterbank on |X|^2 (librosa melspectrogram) instead of |X|
+    log_scale: float = 1.0                      # out = log_scale * log10(max(mul*y + add, log_floor))
+    log_floor: float = 0.0                      # <= 0: no clamp (madmom); librosa power_to_db: amin = 1e-10
     proj_classes: Optional[np.ndarray] = None   # per band class index (or -1), e.g. chroma fold
     proj_matrix: Optional[np.ndarray] = None    # or a dense (B, C) projection
     num_classes: int = 0
@@ -95,7 +98,8 @@ class ResolutionSpec:
             self.frame_size, repr(self.hop_size), self.origin, _digest(self.window32),
             _digest(None if self.filterbank is None else np.asarray(self.filterbank)),
             int(self.log), repr(float(self.mul)), repr(float(self.add)), self.diff_frames,
-            int(self.positive_diffs), int(self.diff_max_bins or 0), _digest(self.proj_off, self.proj_band, self.proj_weight))))
+            int(self.positive_diffs), int(self.diff_max_bins or 0), int(bool(self.power)),
+            repr(float(self.log_scale)), repr(float(self.log_floor)), _digest(self.proj_off, self.proj_band, self.proj_weight))))
 
     @property
     def num_bins(self):
@@ -144,6 +148,7 @@ class DevicePlan:
             r.mul, r.add = float(s.mul), float(s.add)
             r.diff_frames, r.positive_diffs = int(s.diff_frames), int(bool(s.positive_diffs))
             r.diff_max_bins = int(s.diff_max_bins or 0)
+            r.power, r.log_scale, r.log_floor = int(bool(s.power)), float(s.log_scale), float(s.log_floor)
             r.num_classes = int(s.num_classes) if s.proj_off is not None else 0
             if s.proj_off is not None:
                 r.proj_off, r.proj_band, r.proj_weight = iptr(s.proj_off), iptr(s.proj_band), fptr(s.proj_weight)

@@ -43,3 +43,31 @@ def reduce_stats(audio_seconds: float, elapsed_s: float, n_bytes: float, group=N
     dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
     dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
     return float(sums[0]), float(mx[0]), float(sums[1])
+
+
+def bind_to_gpu_numa(device_index: int) -> List[int]:
+    """Pin this process to the CPUs closest to `device_index` (NVML's CPU affinity of the GPU).
+
+    One process per GPU stages its clips through pinned host buffers; Linux places those pages on the
+    NUMA node of the CPU that first touches them, so a rank running on the far socket pushes every
+    byte over the inter-socket link as well as PCIe.  Call this BEFORE allocating pinned memory.
+    Returns the CPU list it bound to ([] when NVML or the affinity call is unavailable -- binding is an
+    optimisation, never a requirement)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+            n_words = (os.cpu_count() + 63) // 64
+            mask = pynvml.nvmlDeviceGetCpuAffinity(handle, n_words)
+        finally:
+            pynvml.nvmlShutdown()
+        cpus = [w * 64 + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return []

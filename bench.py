@@ -197,6 +197,8 @@ def run_ours(args, rank, world, local_rank):
 
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py --impl ours needs a B200; there is no CPU fallback")
+    from audio_tabs_b200.sharding import bind_to_gpu_numa
+    numa_cpus = bind_to_gpu_numa(local_rank)      # pinned staging buffers land on the GPU's NUMA node
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -295,7 +297,7 @@ def run_ours(args, rank, world, local_rank):
         e2e = {"value": world * audio_seconds / (e2e_ms / args.steps * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": int(out_bytes),
                "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps,
-               "api": "audio_tabs_b200.plan.FrontEnd.process_batch_pinned"}
+               "api": "audio_tabs_b200.plan.FrontEnd.process_batch_pinned", "numa_bound_cpus": len(numa_cpus)}
         del host_in, host_out
         if rank == 0:
             pc = pcie_bandwidth(dev)

@@ -95,6 +95,14 @@ typedef struct b200spec_res_desc {
    * b200spec_diff_flux_chroma from the rows b200spec_logfilt wrote (col_diff / d_flux of logfilt must
    * be unused); see FrontEnd.run_packed for the two-call sequence. */
   int32_t diff_max_bins;
+  /* librosa-style variants of the same chain (onset_strength: /root/reference/backend/app/services/
+   * accompaniment/strum.py:114, analysis/content_classifier.py:48,92):
+   *   power      1: the filterbank is applied to |X|^2 (librosa melspectrogram power=2.0); 0: to |X|
+   *   log_scale  out = log_scale * log10(max(mul*y + add, log_floor)); madmom: 1.  power_to_db: 10 with mul 1, add 0
+   *   log_floor  lower clamp of the logarithm's argument (power_to_db amin = 1e-10); <= 0: no clamp */
+  int32_t power;
+  float log_scale;
+  float log_floor;
 } b200spec_res_desc;
 
 typedef struct b200spec_plan_desc {
@@ -174,6 +182,19 @@ int b200spec_logfilt(const b200spec_plan *plan, int32_t res, const void *d_sig, 
  */
 int b200spec_clip_peak(const b200spec_plan *plan, const void *d_sig, const int64_t *d_clip_off, int32_t n_clips,
                        float eps, int32_t reciprocal, float *d_peak, void *stream);
+
+/*
+ * Onset-strength envelope of (log-)filtered rows, librosa.onset.onset_strength semantics
+ * (lag, max_size = 1, detrend = False, center shift):
+ *   Lc = top_db >= 0 ? max(L, max_over_clip(L) - top_db) : L          (power_to_db top_db clip, per clip)
+ *   env[t] = 0                                                     for t < lag + shift
+ *   env[t] = agg_j max(0, Lc[t - shift, j] - Lc[t - shift - lag, j])   otherwise (t < frames of the clip)
+ * aggregate: 0 = mean over the num_bands columns, 1 = median.  shift = n_fft / (2 hop) for center=True.
+ * d_clip_max: n_clips floats of device scratch (receives each clip's maximum).  num_bands <= 1024.
+ */
+int b200spec_onset_envelope(const float *d_L, int64_t ld_L, int32_t num_bands, const int64_t *d_frame_off,
+                            int32_t n_clips, int64_t total_frames, int32_t lag, float top_db, int32_t aggregate,
+                            int32_t shift, float *d_clip_max, float *d_env, void *stream);
 
 /*
  * Stand-alone stages on caller-supplied matrices (used when a madmom chain is not fusable,

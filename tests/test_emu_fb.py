@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from audio_tabs_b200.audio.stft import fft_frequencies
-from audio_tabs_b200.filters import LogarithmicFilterbank, PitchClassProfileFilterbank
+from audio_tabs_b200.filters import LogarithmicFilterbank, PitchClassProfileFilterbank, SlaneyMelFilterbank
 
 ROOT = Path(__file__).resolve().parent.parent
 
@@ -25,6 +25,8 @@ def _banks():
         fb = LogarithmicFilterbank(fft_frequencies(F >> 1, sr), num_bands=nb, fmin=fmin, fmax=fmax, unique_filters=uniq)
         out.append((F, fb.banded()))
     out.append((4096, PitchClassProfileFilterbank(fft_frequencies(2048, sr)).banded()))
+    out.append((2048, SlaneyMelFilterbank(sr, 2048, n_mels=128).banded()))      # librosa onset strength
+    out.append((4096, SlaneyMelFilterbank(22050, 4096, n_mels=64).banded()))
     # one rectangular band over everything, and an empty band between two real ones
     out.append((2048, (np.array([0], np.int32), np.array([1024], np.int32), np.array([0], np.int32),
                        np.full(1024, 1.0 / 1024, np.float32))))

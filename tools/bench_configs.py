@@ -62,6 +62,24 @@ def run(name, spec, n_clips, seconds, dtype="f32", proj=False):
     del sig, out
 
 
+def run_onset(nc, seconds):
+    """librosa-style onset strength (N3): frame 2048, hop 512, 128 mel bands, dB, median envelope."""
+    import numpy as np
+    from audio_tabs_b200.onsets import OnsetStrength
+    dev = torch.device("cuda", 0)
+    n = int(seconds * SR)
+    sig = synth_batch_device(nc, n, seed=9, device=dev)
+    eng = OnsetStrength(sr=SR, aggregate=np.median)
+    packed = Packed(sig, [n] * nc, 512.0, "extend")
+    ms_mel = timeit(lambda: eng.mel_db(packed))
+    ms_all = timeit(lambda: eng.envelope(packed))
+    alg = sig.numel() * 4 + packed.total_frames * 4
+    print(json.dumps({"config": "N3: %dx%ds onset_strength (2048/512, 128 mel, dB, median)" % (nc, seconds), "clips": nc,
+                      "frames": packed.total_frames, "ms": ms_all, "ms_mel_db_only": ms_mel,
+                      "audio_s_per_s": nc * seconds / ms_all * 1e3, "alg_gb": alg / 1e9, "alg_gbs": alg / ms_all / 1e6,
+                      "hbm_frac_of_measured_peak": alg / ms_all / 1e6 / PEAK}), flush=True)
+
+
 def main():
     quick = "--quick" in sys.argv
     nc = 32 if quick else 256
@@ -74,6 +92,7 @@ def main():
         log_filt_spec(8192, 4410.0, 24, 65.0, 2100.0), nc, 180)
     run("key: %dx180s int16 8192 fps5 -> (900,105)" % nc,
         log_filt_spec(8192, 8820.0, 24, 65.0, 2100.0, int16=True), nc, 180, dtype="i16")
+    run_onset(nc, 180)
 
 
 if __name__ == "__main__":
