@@ -69,6 +69,7 @@ struct ResPlan {
   // device tables
   float *d_window = nullptr;
   float2 *d_tw2 = nullptr, *d_tw3 = nullptr, *d_pt = nullptr, *d_wr = nullptr;
+  float2 *d_pair_tw3 = nullptr, *d_pair_wr = nullptr;   // F-point tables of the pair transform (F <= 4096)
   int fb_L = 3, fb_ns = 1, fb_kmin = 0, fb_ndw = 0, fb_ndirect = 0, fb_w4_global = 0;
   float4 *d_fb_w4 = nullptr;
   int4 *d_fb_band = nullptr;
@@ -165,6 +166,21 @@ int build_res(b200spec_plan *pl, const b200spec_res_desc &d, ResPlan &r) {
   if ((rc = upload(pl, tw2.data(), tw2.size(), &r.d_tw2))) return rc;
   if ((rc = upload(pl, tw3.data(), tw3.size(), &r.d_tw3))) return rc;
   if ((rc = upload(pl, pt.data(), pt.size(), &r.d_pt))) return rc;
+  if (F <= 4096) {   // pair transform (two frames as one complex FFT of F points): N' = F, R3' = F / 256
+    const int R3p = F / 256;
+    std::vector<float2> ptw3(129 * R3p), pwr(2 * R3p);
+    for (int q = 0; q <= 128; ++q)
+      for (int n3 = 0; n3 < R3p; ++n3) {
+        double a = -2.0 * PI * (double)(n3 * q) / (double)F;
+        ptw3[n3 * 129 + q] = make_float2((float)cos(a), (float)sin(a));
+      }
+    for (int e = 0; e < 2 * R3p; ++e) {
+      double a = -2.0 * PI * (double)e / (double)(2 * R3p);
+      pwr[e] = make_float2((float)cos(a), (float)sin(a));
+    }
+    if ((rc = upload(pl, ptw3.data(), ptw3.size(), &r.d_pair_tw3))) return rc;
+    if ((rc = upload(pl, pwr.data(), pwr.size(), &r.d_pair_wr))) return rc;
+  }
 
   // banded filterbank -> interleaved slices of at most `seg_max` taps
   const int B = d.num_bands;
@@ -319,6 +335,27 @@ int launch_front(const b200spec_plan *pl, int res, int mode, const void *d_sig, 
   const int in = (pl->dtype == B200SPEC_I16 ? 2 : 0) + (pl->channels == 2 ? 1 : 0);
   const long long task_bound = total_frames / chunk + n_clips;
   cudaError_t e;
+  // The log-filtered path of frames <= 4096 runs the pair kernel (two frames per complex FFT);
+  // B200SPEC_PAIR=0 keeps the one-frame kernel (A/B measurements), as does a configuration whose
+  // tables do not fit next to the larger FFT buffer.
+  static const bool use_pair = []() { const char *v = getenv("B200SPEC_PAIR"); return !(v && v[0] == '0'); }();
+  if (use_pair && mode == b2::MODE_LOGFILT && r.frame_size <= 4096 && r.d_pair_tw3 != nullptr) {
+    b2::FrontParams q = p;
+    q.tw3 = r.d_pair_tw3;
+    q.wr = r.d_pair_wr;
+    switch (r.frame_size) {
+      case 1024: e = b2_launch_pair_1024(in, q, pl->num_sms, task_bound, st); break;
+      case 2048: e = b2_launch_pair_2048(in, q, pl->num_sms, task_bound, st); break;
+      default: e = b2_launch_pair_4096(in, q, pl->num_sms, task_bound, st); break;
+    }
+    if (e == cudaSuccess) {
+      g_launches++;
+      return 0;
+    }
+    if (e != cudaErrorInvalidConfiguration)
+      return fail(B200SPEC_ERR_CUDA, "front-end (pair) kernel launch failed: %s", cudaGetErrorString(e));
+    (void)cudaGetLastError();   // did not fit: fall through to the one-frame kernel
+  }
   switch (r.frame_size) {
     case 1024: e = b2_launch_front_1024(in, mode, p, pl->num_sms, task_bound, st); break;
     case 2048: e = b2_launch_front_2048(in, mode, p, pl->num_sms, task_bound, st); break;

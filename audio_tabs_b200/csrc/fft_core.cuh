@@ -293,4 +293,65 @@ B2_HD float2 fft_pass3_selfpaired(int lane, const float2 *buf, const float2 *wr,
   return make_float2(fmaf(2.f, E.x, T.x), fmaf(2.f, E.y, T.y));
 }
 
+// =================================================================================================
+// Pair transform: TWO real frames of F samples as ONE complex FFT of F points, z[n] = xA[n] + i xB[n]
+// (window folded into the load, pre-scaled by 1/2).  Geometry = FftCfg<2F> (N = F = 16*16*R3).
+//   XA[k] = (Z[k] + conj Z[F-k]) / 2,   XB[k] = -i (Z[k] - conj Z[F-k]) / 2,   k in [0, F/2)
+// With the same column pairing as above (q and 256-q combined BEFORE the last radix: P = a + conj b,
+// M = a - conj b) the two DFT_R3 deliver XA and i*XB directly: no split twiddles, and every one of the
+// 2*R3 outputs is a needed bin -- k3 < R3/2 gives bin q + 256 k3, k3 >= R3/2 gives the conjugate of bin
+// (256-q) + 256 (R3-1-k3).  Only magnitudes are emitted (the fused log-filtered path).
+// -------------------------------------------------------------------------------------------------
+// unit u in [0,127]: pa / pb = columns u and (256-u)&255 (u = 0 pairs column 0 with itself and simply
+// emits bins 256 j twice, plus bin F/2 which lands in the padding of the magnitude buffer).
+// emit(bin, |XA[bin]|, |XB[bin]|) -- the caller takes the magnitudes.
+template <int F2, class Emit>
+B2_HD void fft_pair_pass3_unit(int u, const float2 *pa, const float2 *pb, const float2 *tw3u, Emit emit) {
+  using C = FftCfg<F2>;
+  constexpr int R3 = C::R3;
+  float2 P[R3], M[R3];
+#pragma unroll
+  for (int n3 = 0; n3 < R3; ++n3) {
+    float2 a = pa[n3];
+    float2 b = pb[n3];
+    P[n3] = cadd_conj(a, b);
+    M[n3] = csub_conj(a, b);
+  }
+#pragma unroll
+  for (int n3 = 1; n3 < R3; ++n3) {
+    float2 w = tw3u[n3 * 129];
+    P[n3] = cmul(P[n3], w);
+    M[n3] = cmul(M[n3], w);
+  }
+  Dft<R3>::run(P);
+  Dft<R3>::run(M);
+#pragma unroll
+  for (int k3 = 0; k3 < R3; ++k3) {
+    const int bin = k3 < R3 / 2 ? u + 256 * k3 : ((256 - u) + 256 * (R3 - 1 - k3));
+    emit(bin, P[dft_pos<R3>(k3)], M[dft_pos<R3>(k3)]);
+  }
+}
+
+// The self-paired column q = 128 (bins 128 + 256 j), lane-parallel on R3 lanes of one warp:
+// lane k3 forms Z[128 + 256 k3] = sum_n c[n] W_(2 R3)^(n (2 k3 + 1)); the caller exchanges Z with lane
+// R3-1-k3 (the mirror bin) and emits |Z + conj Z'| (frame A) and |Z - conj Z'| (frame B) for k3 < R3/2.
+template <int F2>
+B2_HD float2 fft_pair_col128(int k3, const float2 *buf, const float2 *wr) {
+  using C = FftCfg<F2>;
+  constexpr int R3 = C::R3;
+  const float2 *c = buf + fft_col_offset<F2>(128);
+  const int step = 2 * k3 + 1;
+  int e = 0;
+  float2 Z = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int n = 0; n < R3; ++n) {
+    const float2 w = wr[e];
+    const float2 cn = c[n];
+    Z.x = fmaf(w.x, cn.x, fmaf(-w.y, cn.y, Z.x));
+    Z.y = fmaf(w.x, cn.y, fmaf(w.y, cn.x, Z.y));
+    e = (e + step) & (2 * R3 - 1);
+  }
+  return Z;
+}
+
 }  // namespace b2

@@ -5,3 +5,7 @@ cudaError_t b2_launch_front_4096(int in, int mode, b2::FrontParams &p, int num_s
                                 cudaStream_t st) {
   return b2::launch_front_size<4096>(in, mode, p, num_sms, task_bound, st);
 }
+
+cudaError_t b2_launch_pair_4096(int in, b2::FrontParams &p, int num_sms, long long task_bound, cudaStream_t st) {
+  return b2::launch_pair_size<4096>(in, p, num_sms, task_bound, st);
+}

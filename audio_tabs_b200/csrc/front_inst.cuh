@@ -2,6 +2,7 @@
 // sizes compile in parallel) and exposes a plain launcher to b200spec.cu.
 #pragma once
 #include "frontend_kernel.cuh"
+#include "frontend_pair_kernel.cuh"
 
 namespace b2 {
 
@@ -52,7 +53,46 @@ static cudaError_t launch_front_size(int in, int mode, FrontParams &p, int num_s
   return cudaErrorInvalidValue;
 }
 
+// groups per CTA of the pair kernel: its FFT buffer holds two frames, so frame 4096 fits three groups
+template <int F>
+struct PairGroupsPerCta {
+#ifndef B2_PAIR_GROUPS_4096
+#define B2_PAIR_GROUPS_4096 3
+#endif
+  static constexpr int value = (F == 4096) ? B2_PAIR_GROUPS_4096 : 4;
+};
+
+// cudaErrorInvalidConfiguration = does not fit in shared memory (the caller falls back to k_front)
+template <int F, int IN>
+static cudaError_t launch_pair_one(FrontParams &p, int num_sms, long long task_bound, cudaStream_t st) {
+  constexpr int G = PairGroupsPerCta<F>::value;
+  const size_t smem = pair_smem_layout<F>(p, G);
+  if (smem > kMaxSmemPerCta) return cudaErrorInvalidConfiguration;
+  auto kern = k_front_pair<F, IN, G>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  long long ctas = (task_bound + G - 1) / G;
+  int grid = (int)(ctas < num_sms ? (ctas < 1 ? 1 : ctas) : num_sms);
+  kern<<<grid, kGroupThreads * G, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+template <int F>
+static cudaError_t launch_pair_size(int in, FrontParams &p, int num_sms, long long task_bound, cudaStream_t st) {
+  switch (in) {
+    case IN_F32_MONO: return launch_pair_one<F, IN_F32_MONO>(p, num_sms, task_bound, st);
+    case IN_F32_STEREO: return launch_pair_one<F, IN_F32_STEREO>(p, num_sms, task_bound, st);
+    case IN_I16_MONO: return launch_pair_one<F, IN_I16_MONO>(p, num_sms, task_bound, st);
+    case IN_I16_STEREO: return launch_pair_one<F, IN_I16_STEREO>(p, num_sms, task_bound, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
 }  // namespace b2
+
+cudaError_t b2_launch_pair_1024(int in, b2::FrontParams &p, int num_sms, long long task_bound, cudaStream_t st);
+cudaError_t b2_launch_pair_2048(int in, b2::FrontParams &p, int num_sms, long long task_bound, cudaStream_t st);
+cudaError_t b2_launch_pair_4096(int in, b2::FrontParams &p, int num_sms, long long task_bound, cudaStream_t st);
 
 // declared here, defined in front_f<F>.cu
 cudaError_t b2_launch_front_1024(int in, int mode, b2::FrontParams &p, int num_sms, long long task_bound, cudaStream_t st);

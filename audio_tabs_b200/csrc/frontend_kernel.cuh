@@ -158,6 +158,142 @@ __device__ __forceinline__ const void *clip_base(const void *sig, long long off)
   return reinterpret_cast<const short2 *>(sig) + off;
 }
 
+// ---- K2/K3 tail shared by k_front and k_front_pair: slab filterbank, band sums, log, lagged difference,
+// stacked stores, flux / projection, for the TB frames whose magnitudes sit in c.s_mags -------------------
+struct TailCtx {
+  const float4 *s_w4;
+  const int4 *s_band;
+  const float *s_dw;
+  float *s_mags, *s_partial, *s_hist, *s_lrow, *s_red;
+  int g, tid;
+};
+
+template <int TB, int TBF, int MS>
+__device__ __forceinline__ int front_tail(const FrontParams &p, const TailCtx &c, int fb, int f0, int f1,
+                                          long long row0, int hslot, float cscale) {
+  const float4 *s_w4 = c.s_w4;
+  const int4 *s_band = c.s_band;
+  const float *s_dw = c.s_dw;
+  float *s_mags = c.s_mags, *s_partial = c.s_partial, *s_hist = c.s_hist, *s_lrow = c.s_lrow, *s_red = c.s_red;
+  const int g = c.g, tid = c.tid;
+  const int B = p.num_bands, kd = p.diff_frames, pstride = p.part_stride;
+#pragma unroll 1
+  for (int h = 0; h < TB; h += TBF) {
+    const int fh = fb + h;
+    if (fh >= f1) break;
+    if (h > 0) group_bar(g);                     // the previous sub-batch is done with s_partial
+    const float *hmags = s_mags + h * MS;
+    // ---- K2a: slab filterbank ----
+    if (p.fb_w4_global) {
+      if (p.power) fb_slabs<15, TBF, MS, true, true>(p.fb_w4, hmags, s_partial, p.fb_ns, p.fb_kmin, pstride, tid);
+      else fb_slabs<15, TBF, MS, true, false>(p.fb_w4, hmags, s_partial, p.fb_ns, p.fb_kmin, pstride, tid);
+    } else if (p.power) {
+      fb_slabs_dispatch<TBF, MS, true>(p.fb_L, s_w4, hmags, s_partial, p.fb_ns, p.fb_kmin, pstride, tid);
+    } else {
+      fb_slabs_dispatch<TBF, MS, false>(p.fb_L, s_w4, hmags, s_partial, p.fb_ns, p.fb_kmin, pstride, tid);
+    }
+    group_bar(g);
+    // ---- K2b/K3: band sum, log10, lagged difference, stacked store ----
+    // lane = band.  Trip counts are made warp-uniform (REDUX max) and lanes past their own count
+    // add 0, so the gather loops carry no divergence.
+    float fluxacc[TBF];
+#pragma unroll
+    for (int t = 0; t < TBF; ++t) fluxacc[t] = 0.f;
+    for (int jb = 0; jb < B; jb += kGroupThreads) {
+      const int j = jb + tid;
+      const bool valid = j < B;
+      const int4 bd = valid ? s_band[j] : make_int4(0, 0, 0, 0);
+      const int nP = __reduce_max_sync(0xffffffffu, bd.y), nD = __reduce_max_sync(0xffffffffu, bd.w);
+      float ysum[TBF];
+#pragma unroll
+      for (int t = 0; t < TBF; ++t) ysum[t] = 0.f;
+      const float *pp = s_partial + bd.x;
+#pragma unroll 4
+      for (int i = 0; i < nP; ++i) {             // slab band: partial sums of the slabs it touches
+        const bool on = i < bd.y;
+#pragma unroll
+        for (int t = 0; t < TBF; ++t) ysum[t] += on ? pp[t * pstride + 4 * i] : 0.f;
+      }
+      const float *dm = hmags + bd.z, *dwp = s_dw + bd.x;
+#pragma unroll 2
+      for (int i = 0; i < nD; ++i) {             // direct band: its few taps straight from the magnitudes
+        const bool on = i < bd.w;
+        const float w = on ? dwp[i] : 0.f;
+#pragma unroll
+        for (int t = 0; t < TBF; ++t) {
+          float m = on ? dm[t * MS + i] : 0.f;
+          if (p.power) m *= m;
+          ysum[t] = fmaf(w, m, ysum[t]);
+        }
+      }
+      if (valid) {
+        float *orow = p.out != nullptr ? p.out + (row0 + fh) * p.ld_out + j : nullptr;
+        int slot = hslot;
+#pragma unroll
+        for (int t = 0; t < TBF; ++t) {
+          const int frame = fh + t;
+          if (frame < f1) {
+            const float y = ysum[t] * cscale;
+            float L = y;
+            if (p.log_enabled) {
+              float a = __fadd_rn(__fmul_rn(p.mul, y), p.add);
+              if (p.log_floor > 0.f) a = fmaxf(a, p.log_floor);
+              L = __log10f(a) * p.log_scale;
+            }
+            float D = 0.f;
+            if (kd > 0) {
+              const float old = s_hist[slot * B + j];
+              s_hist[slot * B + j] = L;
+              if (frame >= kd) D = L - old;
+              if (p.positive) D = fmaxf(D, 0.f);
+              slot = (slot + 1 == kd) ? 0 : slot + 1;
+            }
+            if (p.num_classes > 0) s_lrow[t * B + j] = L;
+            if (frame >= f0) {
+              if (orow != nullptr) {
+                if (p.col_spec >= 0) orow[p.col_spec] = L;
+                if (p.col_diff >= 0) orow[p.col_diff] = D;
+              }
+              fluxacc[t] += D;
+            }
+          }
+          if (orow != nullptr) orow += p.ld_out;
+        }
+      }
+    }
+    if (kd > 0) {                                // ring position of the next step's first frame
+      hslot += TBF;
+      while (hslot >= kd) hslot -= kd;
+    }
+    if (p.flux != nullptr || p.num_classes > 0) {
+      if (p.flux != nullptr) {
+#pragma unroll
+        for (int t = 0; t < TBF; ++t) {
+          float v = fluxacc[t];
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+          if ((tid & 31) == 0) s_red[t * 4 + (tid >> 5)] = v;
+        }
+      }
+      group_bar(g);
+      for (int t = 0; t < TBF; ++t) {
+        const int frame = fh + t;
+        if (frame < f0 || frame >= f1) continue;
+        const long long row = row0 + frame;
+        if (p.flux != nullptr && tid == 0)
+          p.flux[row] = (s_red[t * 4] + s_red[t * 4 + 1]) + (s_red[t * 4 + 2] + s_red[t * 4 + 3]);
+        if (tid < p.num_classes) {
+          float acc = 0.f;
+          for (int i = p.proj_off[tid]; i < p.proj_off[tid + 1]; ++i)
+            acc = fmaf(__ldg(&p.proj_w[i]), s_lrow[t * B + __ldg(&p.proj_band[i])], acc);
+          p.proj[row * p.ld_proj + tid] = acc;
+        }
+      }
+    }
+  }
+  return hslot;
+}
+
 // ---- the front-end kernel ----------------------------------------------------------------------
 template <int F, int IN, int MODE, int G>
 __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams p) {
@@ -208,6 +344,7 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
   float *s_lrow = reinterpret_cast<float *>(gmem + p.g_lrow);
   float *s_red = reinterpret_cast<float *>(gmem + p.g_red);
   volatile int *s_task = reinterpret_cast<volatile int *>(gmem + p.g_task);
+  const TailCtx tctx{s_w4, s_band, s_dw, s_mags, s_partial, s_hist, s_lrow, s_red, g, tid};
 
   // per-thread constants ---------------------------------------------------------------------
   float2 tw2r[16];                       // pass-2 twiddles of this thread's k1
@@ -222,7 +359,7 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
   const int pa_off = fft_col_offset<F>(u), pb_off = fft_col_offset<F>((256 - u) & 255);
 
   const int total_tasks = p.task_off[p.n_clips];
-  const int B = p.num_bands, kd = p.diff_frames, pstride = p.part_stride;
+  const int kd = p.diff_frames;
 
   for (;;) {
     if (tid == 0) *s_task = atomicAdd(p.task_counter, 1);
@@ -343,121 +480,7 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
         group_bar(g);   // pass-3 reads done: buf is free again; magnitudes visible
       }
       // =============== tail for the TB frames of this batch, TBF at a time ===============
-      if (MODE == MODE_LOGFILT)
-#pragma unroll 1
-      for (int h = 0; h < TB; h += TBF) {
-        const int fh = fb + h;
-        if (fh >= f1) break;
-        if (h > 0) group_bar(g);                     // the previous sub-batch is done with s_partial
-        const float *hmags = s_mags + h * MS;
-        // ---- K2a: slab filterbank ----
-        if (p.fb_w4_global) {
-          if (p.power) fb_slabs<15, TBF, MS, true, true>(p.fb_w4, hmags, s_partial, p.fb_ns, p.fb_kmin, pstride, tid);
-          else fb_slabs<15, TBF, MS, true, false>(p.fb_w4, hmags, s_partial, p.fb_ns, p.fb_kmin, pstride, tid);
-        } else if (p.power) {
-          fb_slabs_dispatch<TBF, MS, true>(p.fb_L, s_w4, hmags, s_partial, p.fb_ns, p.fb_kmin, pstride, tid);
-        } else {
-          fb_slabs_dispatch<TBF, MS, false>(p.fb_L, s_w4, hmags, s_partial, p.fb_ns, p.fb_kmin, pstride, tid);
-        }
-        group_bar(g);
-        // ---- K2b/K3: band sum, log10, lagged difference, stacked store ----
-        // lane = band.  Trip counts are made warp-uniform (REDUX max) and lanes past their own count
-        // add 0, so the gather loops carry no divergence.
-        float fluxacc[TBF];
-#pragma unroll
-        for (int t = 0; t < TBF; ++t) fluxacc[t] = 0.f;
-        for (int jb = 0; jb < B; jb += kGroupThreads) {
-          const int j = jb + tid;
-          const bool valid = j < B;
-          const int4 bd = valid ? s_band[j] : make_int4(0, 0, 0, 0);
-          const int nP = __reduce_max_sync(0xffffffffu, bd.y), nD = __reduce_max_sync(0xffffffffu, bd.w);
-          float ysum[TBF];
-#pragma unroll
-          for (int t = 0; t < TBF; ++t) ysum[t] = 0.f;
-          const float *pp = s_partial + bd.x;
-#pragma unroll 4
-          for (int i = 0; i < nP; ++i) {             // slab band: partial sums of the slabs it touches
-            const bool on = i < bd.y;
-#pragma unroll
-            for (int t = 0; t < TBF; ++t) ysum[t] += on ? pp[t * pstride + 4 * i] : 0.f;
-          }
-          const float *dm = hmags + bd.z, *dwp = s_dw + bd.x;
-#pragma unroll 2
-          for (int i = 0; i < nD; ++i) {             // direct band: its few taps straight from the magnitudes
-            const bool on = i < bd.w;
-            const float w = on ? dwp[i] : 0.f;
-#pragma unroll
-            for (int t = 0; t < TBF; ++t) {
-              float m = on ? dm[t * MS + i] : 0.f;
-              if (p.power) m *= m;
-              ysum[t] = fmaf(w, m, ysum[t]);
-            }
-          }
-          if (valid) {
-            float *orow = p.out != nullptr ? p.out + (row0 + fh) * p.ld_out + j : nullptr;
-            int slot = hslot;
-#pragma unroll
-            for (int t = 0; t < TBF; ++t) {
-              const int frame = fh + t;
-              if (frame < f1) {
-                const float y = ysum[t] * cscale;
-                float L = y;
-                if (p.log_enabled) {
-                  float a = __fadd_rn(__fmul_rn(p.mul, y), p.add);
-                  if (p.log_floor > 0.f) a = fmaxf(a, p.log_floor);
-                  L = __log10f(a) * p.log_scale;
-                }
-                float D = 0.f;
-                if (kd > 0) {
-                  const float old = s_hist[slot * B + j];
-                  s_hist[slot * B + j] = L;
-                  if (frame >= kd) D = L - old;
-                  if (p.positive) D = fmaxf(D, 0.f);
-                  slot = (slot + 1 == kd) ? 0 : slot + 1;
-                }
-                if (p.num_classes > 0) s_lrow[t * B + j] = L;
-                if (frame >= f0) {
-                  if (orow != nullptr) {
-                    if (p.col_spec >= 0) orow[p.col_spec] = L;
-                    if (p.col_diff >= 0) orow[p.col_diff] = D;
-                  }
-                  fluxacc[t] += D;
-                }
-              }
-              if (orow != nullptr) orow += p.ld_out;
-            }
-          }
-        }
-        if (kd > 0) {                                // ring position of the next step's first frame
-          hslot += TBF;
-          while (hslot >= kd) hslot -= kd;
-        }
-        if (p.flux != nullptr || p.num_classes > 0) {
-          if (p.flux != nullptr) {
-#pragma unroll
-            for (int t = 0; t < TBF; ++t) {
-              float v = fluxacc[t];
-#pragma unroll
-              for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-              if ((tid & 31) == 0) s_red[t * 4 + (tid >> 5)] = v;
-            }
-          }
-          group_bar(g);
-          for (int t = 0; t < TBF; ++t) {
-            const int frame = fh + t;
-            if (frame < f0 || frame >= f1) continue;
-            const long long row = row0 + frame;
-            if (p.flux != nullptr && tid == 0)
-              p.flux[row] = (s_red[t * 4] + s_red[t * 4 + 1]) + (s_red[t * 4 + 2] + s_red[t * 4 + 3]);
-            if (tid < p.num_classes) {
-              float acc = 0.f;
-              for (int i = p.proj_off[tid]; i < p.proj_off[tid + 1]; ++i)
-                acc = fmaf(__ldg(&p.proj_w[i]), s_lrow[t * B + __ldg(&p.proj_band[i])], acc);
-              p.proj[row * p.ld_proj + tid] = acc;
-            }
-          }
-        }
-      }
+      if (MODE == MODE_LOGFILT) hslot = front_tail<TB, TBF, MS>(p, tctx, fb, f0, f1, row0, hslot, cscale);
     }
   }
 }

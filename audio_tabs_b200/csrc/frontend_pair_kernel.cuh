@@ -1,0 +1,214 @@
+// frontend_pair_kernel.cuh -- the fused log-filtered front end with the PAIR transform: two consecutive
+// real frames of F samples are carried through ONE complex FFT of F points (z = xA + i xB, see the pair
+// section of fft_core.cuh), which removes the even/odd split twiddles, halves the window loads and halves
+// the group barriers per frame compared with k_front (frontend_kernel.cuh).  Same execution model, same
+// tables (plus the F-point twiddles), same tail (front_tail).  MODE_LOGFILT only: the raw STFT keeps k_front.
+//
+// Replaces, for one resolution, the madmom 0.16.1 chain reached from
+// /root/reference/backend/app/services/grid/beats.py:74 (RNNBeatProcessor):
+//   signal_frame -> frame*fft_window -> fftpack.fft[:F/2] -> np.abs -> np.dot(., filterbank)
+//   -> np.log10(mul*y+add) -> SpectrogramDifference(positive) -> np.hstack
+#pragma once
+#include "frontend_kernel.cuh"
+
+namespace b2 {
+
+template <int F>
+struct PairCfg {
+  static_assert(F == 1024 || F == 2048 || F == 4096, "pair transform: frame sizes 1024, 2048, 4096");
+  using C2 = FftCfg<2 * F>;                       // geometry of the F-point complex FFT
+  static constexpr int PPS = C2::FPG;             // pairs per group step
+  static constexpr int FPS = 2 * PPS;             // frames per group step
+  static constexpr int TB = FftCfg<F>::TB >= FPS ? FftCfg<F>::TB : FPS;   // frames per tail batch (multiple of FPS)
+  static constexpr int TBF = TB < 4 ? TB : 4;
+  static constexpr int MS = FftCfg<F>::MS;        // floats per frame in the magnitude buffer
+  static_assert(TB % FPS == 0, "tail batch must hold whole FFT steps");
+};
+
+template <int F>
+inline size_t pair_smem_layout(FrontParams &p, int G) {
+  using P = PairCfg<F>;
+  using C2 = typename P::C2;
+  auto al = [](size_t v) { return (v + 15) & ~size_t(15); };
+  size_t o = 0;
+  p.o_win = (int)o; o = al(o + sizeof(float) * F);
+  p.o_tw3 = (int)o; o = al(o + sizeof(float2) * C2::TW3);
+  p.o_pt = (int)o;                                 // no split twiddles
+  p.o_wr = (int)o;  o = al(o + sizeof(float2) * C2::WR);
+  p.part_stride = p.fb_ns * kGroupThreads * 4;
+  p.o_w4 = (int)o;   o = al(o + (p.fb_w4_global ? 16 : sizeof(float4) * p.fb_ns * p.fb_L * kGroupThreads));
+  p.o_band = (int)o; o = al(o + sizeof(int4) * (p.num_bands > 0 ? p.num_bands : 1));
+  p.o_dw = (int)o;   o = al(o + sizeof(float) * (p.fb_ndw > 0 ? p.fb_ndw : 1));
+  p.o_groups = (int)o;
+  size_t g = 0;
+  g = al(g + sizeof(float2) * P::PPS * C2::BUF);   // in-place FFT buffers (one per pair)
+  p.mag_stride = P::MS;
+  p.g_mags = (int)g;    g = al(g + sizeof(float) * P::TB * P::MS);
+  p.g_partial = (int)g; g = al(g + sizeof(float) * P::TBF * p.part_stride);
+  p.g_hist = (int)g;    g = al(g + sizeof(float) * (p.diff_frames > 0 ? p.diff_frames : 1) * p.num_bands);
+  p.g_lrow = (int)g;    g = al(g + sizeof(float) * P::TBF * p.num_bands);
+  p.g_red = (int)g;     g = al(g + sizeof(float) * 4 * P::TBF);
+  p.g_task = (int)g;    g = al(g + 16);
+  p.group_bytes = (int)g;
+  return o + g * G;
+}
+
+#if defined(__CUDACC__)
+
+template <int F, int IN, int G>
+__global__ void __launch_bounds__(kGroupThreads *G, 1) k_front_pair(const FrontParams p) {
+  using P = PairCfg<F>;
+  using C2 = typename P::C2;
+  constexpr int F2 = 2 * F, PPS = P::PPS, FPS = P::FPS, R3 = C2::R3, S1 = C2::S1, TB = P::TB, TBF = P::TBF, MS = P::MS;
+  extern __shared__ __align__(16) unsigned char smem[];
+  float *s_win = reinterpret_cast<float *>(smem + p.o_win);
+  float2 *s_tw3 = reinterpret_cast<float2 *>(smem + p.o_tw3);
+  float2 *s_wr = reinterpret_cast<float2 *>(smem + p.o_wr);
+  float4 *s_w4 = reinterpret_cast<float4 *>(smem + p.o_w4);
+  int4 *s_band = reinterpret_cast<int4 *>(smem + p.o_band);
+  float *s_dw = reinterpret_cast<float *>(smem + p.o_dw);
+
+  for (int i = threadIdx.x; i < F; i += blockDim.x) s_win[i] = p.window[i];
+  for (int i = threadIdx.x; i < C2::TW3; i += blockDim.x) s_tw3[i] = p.tw3[i];   // F-point tables (pair_tw3 / pair_wr)
+  for (int i = threadIdx.x; i < C2::WR; i += blockDim.x) s_wr[i] = p.wr[i];
+  if (!p.fb_w4_global)
+    for (int i = threadIdx.x; i < p.fb_ns * p.fb_L * kGroupThreads; i += blockDim.x) s_w4[i] = p.fb_w4[i];
+  for (int i = threadIdx.x; i < p.num_bands; i += blockDim.x) s_band[i] = p.fb_band[i];
+  for (int i = threadIdx.x; i < p.fb_ndw; i += blockDim.x) s_dw[i] = p.fb_dw[i];
+  for (int gi = 0; gi < G; ++gi)      // magnitudes (and their padding, which zero-weight taps may read) start out finite
+    for (int i = threadIdx.x; i < TB * MS; i += blockDim.x)
+      reinterpret_cast<float *>(smem + p.o_groups + (size_t)gi * p.group_bytes + p.g_mags)[i] = 0.f;
+  __syncthreads();
+
+  // virtual warp roles rotated by the group number (see k_front)
+  const int g = threadIdx.x / kGroupThreads;
+  const int tid = ((((threadIdx.x >> 5) + g) & 3) << 5) | (threadIdx.x & 31);
+  unsigned char *gmem = smem + p.o_groups + (size_t)g * p.group_bytes;
+  float2 *buf = reinterpret_cast<float2 *>(gmem);
+  float *s_mags = reinterpret_cast<float *>(gmem + p.g_mags);
+  volatile int *s_task = reinterpret_cast<volatile int *>(gmem + p.g_task);
+  const TailCtx tctx{s_w4, s_band, s_dw, s_mags, reinterpret_cast<float *>(gmem + p.g_partial),
+                     reinterpret_cast<float *>(gmem + p.g_hist), reinterpret_cast<float *>(gmem + p.g_lrow),
+                     reinterpret_cast<float *>(gmem + p.g_red), g, tid};
+
+  // per-thread constants ---------------------------------------------------------------------
+  float2 tw2r[16];                       // pass-2 twiddles of this thread's k1
+#pragma unroll
+  for (int n2 = 0; n2 < 16; ++n2) tw2r[n2] = __ldg(&p.tw2[(tid & 15) * 16 + n2]);
+  const int sl12 = (PPS > 1) ? tid / C2::BPF : 0;           // pair slot this thread serves in pass 1/2
+  const int b12 = (PPS > 1) ? tid % C2::BPF : tid;          // butterfly index in pass 1/2 (first iteration)
+  float2 *p1 = buf + sl12 * C2::BUF + b12;                              // pass-1 store base
+  const float *w1 = s_win + b12;                                        // window value of this butterfly's n1 = 0
+  float2 *p2 = buf + sl12 * C2::BUF + (b12 & 15) * S1 + (b12 >> 4);     // pass-2 in-place base (k1, n3)
+  const int u = tid;                                                    // pass-3 unit (0..127, all active)
+  const int pa_off = fft_col_offset<F2>(u), pb_off = fft_col_offset<F2>((256 - u) & 255);
+
+  const int total_tasks = p.task_off[p.n_clips];
+  const int kd = p.diff_frames;
+
+  for (;;) {
+    if (tid == 0) *s_task = atomicAdd(p.task_counter, 1);
+    group_bar(g);
+    const int task = *s_task;
+    group_bar(g);
+    if (task >= total_tasks) break;
+
+    int lo = 0, hi = p.n_clips;          // clip that owns this task: task_off[c] <= task < task_off[c+1]
+    while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (p.task_off[mid] <= task) lo = mid; else hi = mid;
+    }
+    const int c = lo;
+    const long long samp0 = p.clip_off[c];
+    const long long nsamp = p.clip_off[c + 1] - samp0;
+    const long long row0 = p.frame_off[c];
+    const int T = (int)(p.frame_off[c + 1] - row0);
+    const int f0 = (task - p.task_off[c]) * p.chunk;
+    const int f1 = min(T, f0 + p.chunk);
+    const int fs = kd > 0 ? max(0, f0 - kd) : f0;            // warm-up rows for the difference
+    Samples<IN> S{clip_base<IN>(p.sig, samp0)};
+    const float cscale = p.clip_scale != nullptr ? __ldg(p.clip_scale + c) : 1.f;
+
+    int hslot = kd > 0 ? fs % kd : 0;                        // difference ring slot of frame fb
+    for (int fb = fs; fb < f1; fb += TB) {
+      // =============== FFT of the TB frames of this tail batch, FPS frames (PPS pairs) per step ===============
+#pragma unroll 1
+      for (int sub = 0; sub < TB; sub += FPS) {
+        const int f = fb + sub;
+        if (f >= f1) break;
+        // ---------------- pass 1: z[n] = w[n] (xA[n] + i xB[n]), DFT16 ----------------
+        const int fA = f + 2 * sl12;                         // frames of this thread's pair (fB = fA + 1)
+        if (fA < f1) {
+          const long long sA = (long long)((double)fA * p.hop) - (F / 2) - p.origin;
+          const long long sB = (long long)((double)(fA + 1) * p.hop) - (F / 2) - p.origin;
+          const bool hasB = fA + 1 < f1;
+          const bool interior = (sA >= 0) && (sB + F <= nsamp) && hasB;     // sB >= sA
+#pragma unroll 1
+          for (int it = 0; it < C2::IT12; ++it) {
+            const int b = b12 + it * kGroupThreads;
+            const float *wp = w1 + it * kGroupThreads;
+            if (interior) {
+              fft_pass1<F2>([&](int n1) {
+                const float w = wp[n1 * C2::BPF];
+                const int n = n1 * C2::BPF + b;
+                return make_float2(w * S.at(sA + n), w * S.at(sB + n));
+              }, p1 + it * kGroupThreads);
+            } else {
+              fft_pass1<F2>([&](int n1) {
+                const float w = wp[n1 * C2::BPF];
+                const long long a = sA + n1 * C2::BPF + b, bb = sB + n1 * C2::BPF + b;
+                const float xa = (a >= 0 && a < nsamp) ? S.at(a) : 0.f;
+                const float xb = (hasB && bb >= 0 && bb < nsamp) ? S.at(bb) : 0.f;
+                return make_float2(w * xa, w * xb);
+              }, p1 + it * kGroupThreads);
+            }
+          }
+        }
+        if (tid < 32) {
+          // one warp pulls the samples that only the NEXT step's frames touch into L1
+          constexpr int ESZ = (IN == IN_F32_MONO) ? 4 : (IN == IN_F32_STEREO) ? 8 : (IN == IN_I16_MONO) ? 2 : 4;
+          const long long e0 = ((long long)((double)(f + FPS - 1) * p.hop) + (F / 2) - p.origin) * ESZ;
+          long long e1 = ((long long)((double)(f + 2 * FPS - 1) * p.hop) + (F / 2) - p.origin) * ESZ;
+          if (e1 > nsamp * ESZ) e1 = nsamp * ESZ;
+          const char *bytes = reinterpret_cast<const char *>(S.base);
+          for (long long a = (e0 & ~127LL) + tid * 128; a < e1; a += 32 * 128)
+            if (a >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(bytes + a));
+        }
+        group_bar(g);
+        // ---------------- pass 2: twiddle, DFT16, in place ----------------
+        if (fA < f1) {
+#pragma unroll 1
+          for (int it = 0; it < C2::IT12; ++it) fft_pass2<F2>(tw2r, p2 + it * (kGroupThreads >> 4));
+        }
+        group_bar(g);
+        // ---------------- pass 3: last radix on (column u + conj column 256-u): both frames' magnitudes ----------------
+#pragma unroll 1
+        for (int sl = 0; sl < PPS; ++sl) {
+          if (f + 2 * sl >= f1) break;
+          const float2 *fbuf = buf + sl * C2::BUF;
+          float *magsA = s_mags + (sub + 2 * sl) * MS, *magsB = magsA + MS;
+          fft_pair_pass3_unit<F2>(u, fbuf + pa_off, fbuf + pb_off, s_tw3 + u, [&](int bin, float2 xa, float2 xb) {
+            magsA[bin] = cabs_fast(xa);
+            magsB[bin] = cabs_fast(xb);
+          });
+          if (tid < 32) {          // the self-paired column 128: one bin per lane, mirror bin by shuffle
+            const int k3 = tid & (R3 - 1);
+            const float2 Z = fft_pair_col128<F2>(k3, fbuf, s_wr);
+            const float zx = __shfl_sync(0xffffffffu, Z.x, R3 - 1 - k3), zy = __shfl_sync(0xffffffffu, Z.y, R3 - 1 - k3);
+            if (tid < R3 / 2) {
+              magsA[128 + 256 * tid] = cabs_fast(make_float2(Z.x + zx, Z.y - zy));   // |Z + conj Z'|
+              magsB[128 + 256 * tid] = cabs_fast(make_float2(Z.x - zx, Z.y + zy));   // |Z - conj Z'|
+            }
+          }
+        }
+        group_bar(g);   // pass-3 reads done before the next pass 1 overwrites buf; magnitudes visible
+      }
+      // =============== tail for the TB frames of this batch ===============
+      hslot = front_tail<TB, TBF, MS>(p, tctx, fb, f0, f1, row0, hslot, cscale);
+    }
+  }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace b2
