@@ -23,6 +23,34 @@ static inline float4 make_float4(float x, float y, float z, float w) {
 
 namespace b2 {
 
+// ---- where the magnitude of (bin k, frame t of the batch) lives ------------------------------------
+// MagLinear: frame t is a row of MS floats (k_front, and k_front_pair for frames <= 2048).
+template <int MS_>
+struct MagLinear {
+  static constexpr int MS = MS_;
+  template <int TBF>
+  static B2_HD void load(const float *mags, int k, float (&m)[TBF]) {
+#pragma unroll
+    for (int t = 0; t < TBF; ++t) m[t] = mags[t * MS + k];
+  }
+};
+// MagInPlace: k_front_pair for frame 4096 has no room for a separate magnitude buffer; pass 3 overwrites
+// the FFT columns it has just consumed: bin k = q + 256 j of frames (A, B) sits at floats
+// 2 * column_offset(q) + 2 j + {0, 1} of the pair's buffer (F2 = 2 * frame size).  Both frames come with
+// one 64-bit load.
+template <int F2, int MS_>
+struct MagInPlace {
+  static constexpr int MS = MS_;
+  static B2_HD int at(int k) { return 2 * fft_col_offset<F2>(k & 255) + 2 * (k >> 8); }
+  template <int TBF>
+  static B2_HD void load(const float *mags, int k, float (&m)[TBF]) {
+    static_assert(TBF == 2, "in-place magnitudes hold exactly one pair of frames");
+    const float2 v = *reinterpret_cast<const float2 *>(mags + at(k));
+    m[0] = v.x;
+    m[1] = v.y;
+  }
+};
+
 // Thread `tid` walks the L consecutive bins of each of its slabs once, for TBF frames at a time:
 // one 128-bit weight load per bin (shared by the frames), one magnitude load per bin and frame, four
 // FMAs per bin and frame.  Neighbouring lanes sit L (odd) bins apart: no bank conflicts, no
@@ -30,14 +58,14 @@ namespace b2 {
 // for the band with index r modulo 4.
 // W4G: the weight table did not fit in shared memory and is read from global memory (read-only path).
 // POW: the filterbank works on the power spectrum: every magnitude is squared as it is read.
-template <int L, int TBF, int MS, bool W4G = false, bool POW = false>
+template <int L, int TBF, class MA, bool W4G = false, bool POW = false>
 B2_HD void fb_slabs(const float4 *s_w4, const float *s_mags, float *s_part, int ns, int kmin, int pstride, int tid) {
+  constexpr int MS = MA::MS;
   for (int s = 0; s < ns; ++s) {
     const int g = s * kGroupThreads + tid;
     int k0 = kmin + g * L;
     if (k0 > MS - L) k0 = MS - L;                // slabs past the spectrum carry zero weights
     const float4 *wp = s_w4 + s * L * kGroupThreads + tid;
-    const float *mp = s_mags + k0;
     float4 acc[TBF];
 #pragma unroll
     for (int t = 0; t < TBF; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -48,9 +76,11 @@ B2_HD void fb_slabs(const float4 *s_w4, const float *s_mags, float *s_part, int 
 #else
       const float4 w = wp[i * kGroupThreads];
 #endif
+      float mm[TBF];
+      MA::load(s_mags, k0 + i, mm);
 #pragma unroll
       for (int t = 0; t < TBF; ++t) {
-        float m = mp[t * MS + i];
+        float m = mm[t];
         if (POW) m *= m;
         acc[t].x = fmaf(w.x, m, acc[t].x);
         acc[t].y = fmaf(w.y, m, acc[t].y);
@@ -63,22 +93,22 @@ B2_HD void fb_slabs(const float4 *s_w4, const float *s_mags, float *s_part, int 
   }
 }
 
-template <int TBF, int MS, bool POW = false>
+template <int TBF, class MA, bool POW = false>
 B2_HD void fb_slabs_dispatch(int L, const float4 *s_w4, const float *s_mags, float *s_part, int ns, int kmin,
                              int pstride, int tid) {
   switch (L) {
-    case 3: fb_slabs<3, TBF, MS, false, POW>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
-    case 5: fb_slabs<5, TBF, MS, false, POW>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
-    case 7: fb_slabs<7, TBF, MS, false, POW>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
-    case 9: fb_slabs<9, TBF, MS, false, POW>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
-    case 11: fb_slabs<11, TBF, MS, false, POW>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
-    case 13: fb_slabs<13, TBF, MS, false, POW>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
-    default: fb_slabs<15, TBF, MS, false, POW>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
+    case 3: fb_slabs<3, TBF, MA, false, POW>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
+    case 5: fb_slabs<5, TBF, MA, false, POW>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
+    case 7: fb_slabs<7, TBF, MA, false, POW>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
+    case 9: fb_slabs<9, TBF, MA, false, POW>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
+    case 11: fb_slabs<11, TBF, MA, false, POW>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
+    case 13: fb_slabs<13, TBF, MA, false, POW>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
+    default: fb_slabs<15, TBF, MA, false, POW>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
   }
 }
 
 // band sums of TBF frames for the band described by bd (FbBand in fb_pack.h)
-template <int TBF, int MS>
+template <int TBF, class MA>
 B2_HD void fb_band_sum(const int4 bd, const float *s_part, int pstride, const float *s_mags, const float *s_dw,
                        float (&ysum)[TBF]) {
 #pragma unroll
@@ -88,11 +118,12 @@ B2_HD void fb_band_sum(const int4 bd, const float *s_part, int pstride, const fl
 #pragma unroll
     for (int t = 0; t < TBF; ++t) ysum[t] += pp[t * pstride + 4 * i];
   }
-  const float *dm = s_mags + bd.z;
   for (int i = 0; i < bd.w; ++i) {               // direct band: its few taps straight from the magnitudes
     const float w = s_dw[bd.x + i];
+    float mm[TBF];
+    MA::load(s_mags, bd.z + i, mm);
 #pragma unroll
-    for (int t = 0; t < TBF; ++t) ysum[t] = fmaf(w, dm[t * MS + i], ysum[t]);
+    for (int t = 0; t < TBF; ++t) ysum[t] = fmaf(w, mm[t], ysum[t]);
   }
 }
 

@@ -52,7 +52,9 @@ struct FftCfg {
   static constexpr int PT = 129 * R3;      // pt[k3*129 + q] = -i * W_F^(q + 256*k3)
   static constexpr int WR = 2 * R3;        // wr[e] = W_(2 R3)^e, used by the self-paired columns
   // frames per tail batch (filterbank/log/diff stage): 4, 4, 2, 1 -- measured best on B200 (profiles/README.md)
-#ifdef B2_TAIL_STEPS
+#if defined(B2_TB_1024) && defined(B2_TB_2048) && defined(B2_TB_4096)   // tuning override
+  static constexpr int TB = (F == 1024) ? B2_TB_1024 : (F == 2048) ? B2_TB_2048 : (F == 4096) ? B2_TB_4096 : 1;
+#elif defined(B2_TAIL_STEPS)
   static constexpr int TB = (F == 8192) ? 1 : B2_TAIL_STEPS * FPG;
 #else
   static constexpr int TB = (F == 1024) ? 4 : (F == 2048) ? 4 : (F == 4096) ? 2 : 1;

@@ -57,7 +57,11 @@ static cudaError_t launch_front_size(int in, int mode, FrontParams &p, int num_s
 template <int F>
 struct PairGroupsPerCta {
 #ifndef B2_PAIR_GROUPS_4096
+#ifdef B2_PAIR_INPLACE
+#define B2_PAIR_GROUPS_4096 4     // magnitudes in place of the consumed FFT columns (PairCfg::INPLACE)
+#else
 #define B2_PAIR_GROUPS_4096 3
+#endif
 #endif
   static constexpr int value = (F == 4096) ? B2_PAIR_GROUPS_4096 : 4;
 };

@@ -168,7 +168,7 @@ struct TailCtx {
   int g, tid;
 };
 
-template <int TB, int TBF, int MS>
+template <int TB, int TBF, class MA>
 __device__ __forceinline__ int front_tail(const FrontParams &p, const TailCtx &c, int fb, int f0, int f1,
                                           long long row0, int hslot, float cscale) {
   const float4 *s_w4 = c.s_w4;
@@ -177,6 +177,7 @@ __device__ __forceinline__ int front_tail(const FrontParams &p, const TailCtx &c
   float *s_mags = c.s_mags, *s_partial = c.s_partial, *s_hist = c.s_hist, *s_lrow = c.s_lrow, *s_red = c.s_red;
   const int g = c.g, tid = c.tid;
   const int B = p.num_bands, kd = p.diff_frames, pstride = p.part_stride;
+  constexpr int MS = MA::MS;
 #pragma unroll 1
   for (int h = 0; h < TB; h += TBF) {
     const int fh = fb + h;
@@ -185,12 +186,12 @@ __device__ __forceinline__ int front_tail(const FrontParams &p, const TailCtx &c
     const float *hmags = s_mags + h * MS;
     // ---- K2a: slab filterbank ----
     if (p.fb_w4_global) {
-      if (p.power) fb_slabs<15, TBF, MS, true, true>(p.fb_w4, hmags, s_partial, p.fb_ns, p.fb_kmin, pstride, tid);
-      else fb_slabs<15, TBF, MS, true, false>(p.fb_w4, hmags, s_partial, p.fb_ns, p.fb_kmin, pstride, tid);
+      if (p.power) fb_slabs<15, TBF, MA, true, true>(p.fb_w4, hmags, s_partial, p.fb_ns, p.fb_kmin, pstride, tid);
+      else fb_slabs<15, TBF, MA, true, false>(p.fb_w4, hmags, s_partial, p.fb_ns, p.fb_kmin, pstride, tid);
     } else if (p.power) {
-      fb_slabs_dispatch<TBF, MS, true>(p.fb_L, s_w4, hmags, s_partial, p.fb_ns, p.fb_kmin, pstride, tid);
+      fb_slabs_dispatch<TBF, MA, true>(p.fb_L, s_w4, hmags, s_partial, p.fb_ns, p.fb_kmin, pstride, tid);
     } else {
-      fb_slabs_dispatch<TBF, MS, false>(p.fb_L, s_w4, hmags, s_partial, p.fb_ns, p.fb_kmin, pstride, tid);
+      fb_slabs_dispatch<TBF, MA, false>(p.fb_L, s_w4, hmags, s_partial, p.fb_ns, p.fb_kmin, pstride, tid);
     }
     group_bar(g);
     // ---- K2b/K3: band sum, log10, lagged difference, stacked store ----
@@ -214,14 +215,18 @@ __device__ __forceinline__ int front_tail(const FrontParams &p, const TailCtx &c
 #pragma unroll
         for (int t = 0; t < TBF; ++t) ysum[t] += on ? pp[t * pstride + 4 * i] : 0.f;
       }
-      const float *dm = hmags + bd.z, *dwp = s_dw + bd.x;
+      const float *dwp = s_dw + bd.x;
 #pragma unroll 2
       for (int i = 0; i < nD; ++i) {             // direct band: its few taps straight from the magnitudes
         const bool on = i < bd.w;
         const float w = on ? dwp[i] : 0.f;
+        float mm[TBF];
+#pragma unroll
+        for (int t = 0; t < TBF; ++t) mm[t] = 0.f;
+        if (on) MA::load(hmags, bd.z + i, mm);
 #pragma unroll
         for (int t = 0; t < TBF; ++t) {
-          float m = on ? dm[t * MS + i] : 0.f;
+          float m = mm[t];
           if (p.power) m *= m;
           ysum[t] = fmaf(w, m, ysum[t]);
         }
@@ -480,7 +485,7 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
         group_bar(g);   // pass-3 reads done: buf is free again; magnitudes visible
       }
       // =============== tail for the TB frames of this batch, TBF at a time ===============
-      if (MODE == MODE_LOGFILT) hslot = front_tail<TB, TBF, MS>(p, tctx, fb, f0, f1, row0, hslot, cscale);
+      if (MODE == MODE_LOGFILT) hslot = front_tail<TB, TBF, MagLinear<MS>>(p, tctx, fb, f0, f1, row0, hslot, cscale);
     }
   }
 }

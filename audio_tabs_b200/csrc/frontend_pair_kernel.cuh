@@ -9,6 +9,8 @@
 //   signal_frame -> frame*fft_window -> fftpack.fft[:F/2] -> np.abs -> np.dot(., filterbank)
 //   -> np.log10(mul*y+add) -> SpectrogramDifference(positive) -> np.hstack
 #pragma once
+#include <type_traits>
+
 #include "frontend_kernel.cuh"
 
 namespace b2 {
@@ -22,7 +24,19 @@ struct PairCfg {
   static constexpr int TB = FftCfg<F>::TB >= FPS ? FftCfg<F>::TB : FPS;   // frames per tail batch (multiple of FPS)
   static constexpr int TBF = TB < 4 ? TB : 4;
   static constexpr int MS = FftCfg<F>::MS;        // floats per frame in the magnitude buffer
+  // Frame 4096: a 33 KB FFT buffer per pair plus 16 KB of magnitudes allow three groups per SM only.
+  // -DB2_PAIR_INPLACE makes pass 3 write the magnitudes IN PLACE of the columns it has consumed
+  // (MagInPlace) so that four groups fit; measured on B200 it loses (7.67 ms against 7.54 ms for three
+  // groups with 163 registers: the scattered addressing and the extra barrier cost more than the fourth
+  // group brings), so it is off by default.
+#ifdef B2_PAIR_INPLACE
+  static constexpr bool INPLACE = (F == 4096);
+#else
+  static constexpr bool INPLACE = false;
+#endif
+  using MA = typename std::conditional<INPLACE, MagInPlace<2 * F, MS>, MagLinear<MS>>::type;
   static_assert(TB % FPS == 0, "tail batch must hold whole FFT steps");
+  static_assert(!INPLACE || (TB == FPS && PPS == 1), "in-place magnitudes: one pair per tail batch");
 };
 
 template <int F>
@@ -43,7 +57,8 @@ inline size_t pair_smem_layout(FrontParams &p, int G) {
   size_t g = 0;
   g = al(g + sizeof(float2) * P::PPS * C2::BUF);   // in-place FFT buffers (one per pair)
   p.mag_stride = P::MS;
-  p.g_mags = (int)g;    g = al(g + sizeof(float) * P::TB * P::MS);
+  p.g_mags = 0;         // in place: the magnitudes live in the FFT buffer
+  if (!P::INPLACE) { p.g_mags = (int)g; g = al(g + sizeof(float) * P::TB * P::MS); }
   p.g_partial = (int)g; g = al(g + sizeof(float) * P::TBF * p.part_stride);
   p.g_hist = (int)g;    g = al(g + sizeof(float) * (p.diff_frames > 0 ? p.diff_frames : 1) * p.num_bands);
   p.g_lrow = (int)g;    g = al(g + sizeof(float) * P::TBF * p.num_bands);
@@ -76,7 +91,7 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front_pair(const FrontP
   for (int i = threadIdx.x; i < p.num_bands; i += blockDim.x) s_band[i] = p.fb_band[i];
   for (int i = threadIdx.x; i < p.fb_ndw; i += blockDim.x) s_dw[i] = p.fb_dw[i];
   for (int gi = 0; gi < G; ++gi)      // magnitudes (and their padding, which zero-weight taps may read) start out finite
-    for (int i = threadIdx.x; i < TB * MS; i += blockDim.x)
+    for (int i = threadIdx.x; i < (P::INPLACE ? 2 * C2::BUF : TB * MS); i += blockDim.x)
       reinterpret_cast<float *>(smem + p.o_groups + (size_t)gi * p.group_bytes + p.g_mags)[i] = 0.f;
   __syncthreads();
 
@@ -187,24 +202,29 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front_pair(const FrontP
           if (f + 2 * sl >= f1) break;
           const float2 *fbuf = buf + sl * C2::BUF;
           float *magsA = s_mags + (sub + 2 * sl) * MS, *magsB = magsA + MS;
-          fft_pair_pass3_unit<F2>(u, fbuf + pa_off, fbuf + pb_off, s_tw3 + u, [&](int bin, float2 xa, float2 xb) {
-            magsA[bin] = cabs_fast(xa);
-            magsB[bin] = cabs_fast(xb);
-          });
+          auto put = [&](int bin, float ma, float mb) {
+            if (P::INPLACE) {
+              *reinterpret_cast<float2 *>(s_mags + MagInPlace<F2, MS>::at(bin)) = make_float2(ma, mb);
+            } else {
+              magsA[bin] = ma;
+              magsB[bin] = mb;
+            }
+          };
+          fft_pair_pass3_unit<F2>(u, fbuf + pa_off, fbuf + pb_off, s_tw3 + u,
+                                  [&](int bin, float2 xa, float2 xb) { put(bin, cabs_fast(xa), cabs_fast(xb)); });
           if (tid < 32) {          // the self-paired column 128: one bin per lane, mirror bin by shuffle
             const int k3 = tid & (R3 - 1);
             const float2 Z = fft_pair_col128<F2>(k3, fbuf, s_wr);
             const float zx = __shfl_sync(0xffffffffu, Z.x, R3 - 1 - k3), zy = __shfl_sync(0xffffffffu, Z.y, R3 - 1 - k3);
-            if (tid < R3 / 2) {
-              magsA[128 + 256 * tid] = cabs_fast(make_float2(Z.x + zx, Z.y - zy));   // |Z + conj Z'|
-              magsB[128 + 256 * tid] = cabs_fast(make_float2(Z.x - zx, Z.y + zy));   // |Z - conj Z'|
-            }
+            if (tid < R3 / 2)       // |Z + conj Z'| (frame A), |Z - conj Z'| (frame B)
+              put(128 + 256 * tid, cabs_fast(make_float2(Z.x + zx, Z.y - zy)), cabs_fast(make_float2(Z.x - zx, Z.y + zy)));
           }
         }
         group_bar(g);   // pass-3 reads done before the next pass 1 overwrites buf; magnitudes visible
       }
       // =============== tail for the TB frames of this batch ===============
-      hslot = front_tail<TB, TBF, MS>(p, tctx, fb, f0, f1, row0, hslot, cscale);
+      hslot = front_tail<TB, TBF, typename P::MA>(p, tctx, fb, f0, f1, row0, hslot, cscale);
+      if (P::INPLACE) group_bar(g);   // the band stage has read its magnitudes before pass 1 overwrites the buffer
     }
   }
 }

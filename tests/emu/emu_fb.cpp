@@ -34,14 +34,14 @@ int run(int B, const std::vector<int> &st, const std::vector<int> &ln, const std
   const int pstride = P.NS * 128 * 4;
   std::vector<float> part((size_t)TBF * pstride, -1.f);
   for (int tid = 0; tid < 128; ++tid)
-    b2::fb_slabs_dispatch<TBF, MS>(P.L, reinterpret_cast<const float4 *>(P.w4.data()), mags.data(), part.data(), P.NS,
+    b2::fb_slabs_dispatch<TBF, b2::MagLinear<MS>>(P.L, reinterpret_cast<const float4 *>(P.w4.data()), mags.data(), part.data(), P.NS,
                                    P.kmin, pstride, tid);
   double worst = 0;
   for (int j = 0; j < B; ++j) {
     float y[TBF];
     int4 bd;
     bd.x = P.band[j].x; bd.y = P.band[j].y; bd.z = P.band[j].z; bd.w = P.band[j].w;
-    b2::fb_band_sum<TBF, MS>(bd, part.data(), pstride, mags.data(), P.dw.data(), y);
+    b2::fb_band_sum<TBF, b2::MagLinear<MS>>(bd, part.data(), pstride, mags.data(), P.dw.data(), y);
     for (int t = 0; t < TBF; ++t) {
       double ref = 0;
       for (int i = 0; i < ln[j]; ++i) ref += (double)w[wo[j] + i] * mags[(size_t)t * MS + st[j] + i];
