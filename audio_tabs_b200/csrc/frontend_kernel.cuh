@@ -148,6 +148,28 @@ struct Samples {
       return (float)(((int)v.x + (int)v.y) / 2);      // float64 mean cast back to int16: truncation
     }
   }
+  // Address of sample s, formed ONCE; at_ptr(q, off) then loads sample s + off with `off` folded into
+  // the load's immediate field (off is a compile-time constant at every call site) instead of fresh
+  // 64-bit address arithmetic per load.
+  __device__ __forceinline__ const void *ptr(long long s) const {
+    if (IN == IN_F32_MONO) return reinterpret_cast<const float *>(base) + s;
+    if (IN == IN_F32_STEREO) return reinterpret_cast<const float2 *>(base) + s;
+    if (IN == IN_I16_MONO) return reinterpret_cast<const short *>(base) + s;
+    return reinterpret_cast<const short2 *>(base) + s;
+  }
+  static __device__ __forceinline__ float at_ptr(const void *q, int off) {
+    if (IN == IN_F32_MONO) {
+      return __ldg(reinterpret_cast<const float *>(q) + off);
+    } else if (IN == IN_F32_STEREO) {
+      float2 v = __ldg(reinterpret_cast<const float2 *>(q) + off);
+      return (v.x + v.y) * 0.5f;
+    } else if (IN == IN_I16_MONO) {
+      return (float)__ldg(reinterpret_cast<const short *>(q) + off);
+    } else {
+      short2 v = __ldg(reinterpret_cast<const short2 *>(q) + off);
+      return (float)(((int)v.x + (int)v.y) / 2);
+    }
+  }
 };
 
 template <int IN>
@@ -407,9 +429,10 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
               const long long sb = s0 + 2 * (b12 + it * kGroupThreads);
               const float *wp = w1 + 2 * it * kGroupThreads;
               if (interior) {
+                const void *q = S.ptr(sb);
                 fft_pass1<F>([&](int n1) {
                   float2 w = *reinterpret_cast<const float2 *>(wp + 2 * n1 * C::BPF);
-                  return emul(w, make_float2(S.at(sb + 2 * n1 * C::BPF), S.at(sb + 2 * n1 * C::BPF + 1)));
+                  return emul(w, make_float2(Samples<IN>::at_ptr(q, 2 * n1 * C::BPF), Samples<IN>::at_ptr(q, 2 * n1 * C::BPF + 1)));
                 }, p1 + it * kGroupThreads);
               } else {
                 fft_pass1<F>([&](int n1) {

@@ -163,10 +163,10 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front_pair(const FrontP
             const int b = b12 + it * kGroupThreads;
             const float *wp = w1 + it * kGroupThreads;
             if (interior) {
+              const void *qa = S.ptr(sA + b), *qb = S.ptr(sB + b);
               fft_pass1<F2>([&](int n1) {
                 const float w = wp[n1 * C2::BPF];
-                const int n = n1 * C2::BPF + b;
-                return make_float2(w * S.at(sA + n), w * S.at(sB + n));
+                return make_float2(w * Samples<IN>::at_ptr(qa, n1 * C2::BPF), w * Samples<IN>::at_ptr(qb, n1 * C2::BPF));
               }, p1 + it * kGroupThreads);
             } else {
               fft_pass1<F2>([&](int n1) {
