@@ -266,6 +266,9 @@ int choose_chunk(const b200spec_plan *pl, int F, long long total_frames, int kd)
   const int lo = kd > 0 ? 16 : 4;
   if (chunk < lo) chunk = lo;
   if (chunk > 96) chunk = 96;     // measured on B200: 64-96 frames per task balance warm-up rows and tail imbalance
+  // a task transforms chunk + kd frames (kd warm-up rows of the difference); keep that a multiple of the
+  // tail batch (4 frames, pairs of frames in k_front_pair) so no step runs half empty
+  if (chunk >= 16) chunk -= (chunk + kd) % 4;
   if (const char *e = getenv("B200SPEC_CHUNK")) {   // tuning override
     const int v = atoi(e);
     if (v > 0) chunk = v;
