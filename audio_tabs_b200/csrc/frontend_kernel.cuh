@@ -129,6 +129,12 @@ __device__ __forceinline__ float fast_sqrt(float v) {
   return r;
 }
 
+__device__ __forceinline__ float fast_lg2(float v) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));   // one MUFU; the argument is >= add (or the floor) here
+  return r;
+}
+
 __device__ __forceinline__ float cabs_fast(float2 X) { return fast_sqrt(fmaf(X.x, X.x, X.y * X.y)); }
 
 // ---- sample access: madmom Signal dtype + remix (audio/signal.py) ------------------------------
@@ -188,6 +194,21 @@ struct TailCtx {
   const float *s_dw;
   float *s_mags, *s_partial, *s_hist, *s_lrow, *s_red;
   int g, tid;
+  // band-stage constants, resolved once per kernel instead of per output element
+  float *out_spec, *out_diff;     // p.out + col_spec / + col_diff, or nullptr when that half is not wanted
+  bool do_log, positive;
+  float lmul, ladd, lfloor, lk;   // lk = log_scale * log10(2): log10(a) = lg2(a) * log10(2)
+
+  __device__ __forceinline__ void resolve(const FrontParams &p) {
+    out_spec = (p.out != nullptr && p.col_spec >= 0) ? p.out + p.col_spec : nullptr;
+    out_diff = (p.out != nullptr && p.col_diff >= 0) ? p.out + p.col_diff : nullptr;
+    do_log = p.log_enabled != 0;
+    positive = p.positive != 0;
+    lmul = p.mul;
+    ladd = p.add;
+    lfloor = p.log_floor;
+    lk = p.log_scale * 0.30102999566398120f;
+  }
 };
 
 template <int TB, int TBF, class MA>
@@ -222,6 +243,8 @@ __device__ __forceinline__ int front_tail(const FrontParams &p, const TailCtx &c
     float fluxacc[TBF];
 #pragma unroll
     for (int t = 0; t < TBF; ++t) fluxacc[t] = 0.f;
+    const int nvalid = min(TBF, f1 - fh);        // frames of this sub-batch that exist
+    const int nskip = max(0, f0 - fh);           // leading warm-up frames: they only feed the difference ring
     for (int jb = 0; jb < B; jb += kGroupThreads) {
       const int j = jb + tid;
       const bool valid = j < B;
@@ -254,37 +277,39 @@ __device__ __forceinline__ int front_tail(const FrontParams &p, const TailCtx &c
         }
       }
       if (valid) {
-        float *orow = p.out != nullptr ? p.out + (row0 + fh) * p.ld_out + j : nullptr;
+        // the two output pointers of this band for the first frame of the sub-batch (advanced by ld_out)
+        float *ps = c.out_spec + (row0 + fh) * p.ld_out + j;
+        float *pd = c.out_diff + (row0 + fh) * p.ld_out + j;
+        float *hp = s_hist + hslot * B + j;
         int slot = hslot;
 #pragma unroll
         for (int t = 0; t < TBF; ++t) {
-          const int frame = fh + t;
-          if (frame < f1) {
-            const float y = ysum[t] * cscale;
-            float L = y;
-            if (p.log_enabled) {
-              float a = __fadd_rn(__fmul_rn(p.mul, y), p.add);
-              if (p.log_floor > 0.f) a = fmaxf(a, p.log_floor);
-              L = __log10f(a) * p.log_scale;
+          if (t < nvalid) {
+            float L = ysum[t] * cscale;
+            if (c.do_log) {
+              float a = __fadd_rn(__fmul_rn(c.lmul, L), c.ladd);    // separate multiply and add, as numpy
+              if (c.lfloor > 0.f) a = fmaxf(a, c.lfloor);
+              L = fast_lg2(a) * c.lk;                               // log_scale * log10(a)
             }
             float D = 0.f;
             if (kd > 0) {
-              const float old = s_hist[slot * B + j];
-              s_hist[slot * B + j] = L;
-              if (frame >= kd) D = L - old;
-              if (p.positive) D = fmaxf(D, 0.f);
-              slot = (slot + 1 == kd) ? 0 : slot + 1;
+              const float old = *hp;
+              *hp = L;
+              if (fh + t >= kd) D = L - old;
+              if (c.positive) D = fmaxf(D, 0.f);
+              ++slot;
+              hp += B;
+              if (slot == kd) slot = 0, hp -= kd * B;
             }
             if (p.num_classes > 0) s_lrow[t * B + j] = L;
-            if (frame >= f0) {
-              if (orow != nullptr) {
-                if (p.col_spec >= 0) orow[p.col_spec] = L;
-                if (p.col_diff >= 0) orow[p.col_diff] = D;
-              }
+            if (t >= nskip) {
+              if (c.out_spec != nullptr) *ps = L;
+              if (c.out_diff != nullptr) *pd = D;
               fluxacc[t] += D;
             }
           }
-          if (orow != nullptr) orow += p.ld_out;
+          ps += p.ld_out;
+          pd += p.ld_out;
         }
       }
     }
@@ -371,7 +396,8 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
   float *s_lrow = reinterpret_cast<float *>(gmem + p.g_lrow);
   float *s_red = reinterpret_cast<float *>(gmem + p.g_red);
   volatile int *s_task = reinterpret_cast<volatile int *>(gmem + p.g_task);
-  const TailCtx tctx{s_w4, s_band, s_dw, s_mags, s_partial, s_hist, s_lrow, s_red, g, tid};
+  TailCtx tctx{s_w4, s_band, s_dw, s_mags, s_partial, s_hist, s_lrow, s_red, g, tid};
+  tctx.resolve(p);
 
   // per-thread constants ---------------------------------------------------------------------
   float2 tw2r[16];                       // pass-2 twiddles of this thread's k1

@@ -102,9 +102,10 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front_pair(const FrontP
   float2 *buf = reinterpret_cast<float2 *>(gmem);
   float *s_mags = reinterpret_cast<float *>(gmem + p.g_mags);
   volatile int *s_task = reinterpret_cast<volatile int *>(gmem + p.g_task);
-  const TailCtx tctx{s_w4, s_band, s_dw, s_mags, reinterpret_cast<float *>(gmem + p.g_partial),
-                     reinterpret_cast<float *>(gmem + p.g_hist), reinterpret_cast<float *>(gmem + p.g_lrow),
-                     reinterpret_cast<float *>(gmem + p.g_red), g, tid};
+  TailCtx tctx{s_w4, s_band, s_dw, s_mags, reinterpret_cast<float *>(gmem + p.g_partial),
+               reinterpret_cast<float *>(gmem + p.g_hist), reinterpret_cast<float *>(gmem + p.g_lrow),
+               reinterpret_cast<float *>(gmem + p.g_red), g, tid};
+  tctx.resolve(p);
 
   // per-thread constants ---------------------------------------------------------------------
   float2 tw2r[16];                       // pass-2 twiddles of this thread's k1
