@@ -215,6 +215,8 @@ int build_res(b200spec_plan *pl, const b200spec_res_desc &d, ResPlan &r) {
       case 4096: need = b2::front_smem_layout<4096>(probe, b2::MODE_LOGFILT, b2::GroupsPerCta<4096>::value); break;
       default: need = b2::front_smem_layout<8192>(probe, b2::MODE_LOGFILT, b2::GroupsPerCta<8192>::value); break;
     }
+    if (const char *e = getenv("B200SPEC_W4_GLOBAL"))   // tuning override: force the global-memory table
+      if (e[0] == '1') need = b2::kMaxSmemPerCta + 1;
     if (need > b2::kMaxSmemPerCta) {   // keep the table in global memory (one fixed slab length)
       fp = b2::fb_pack(N, B, d.band_start, d.band_len, d.band_woff, d.weights, TBF, 15);
       r.fb_w4_global = 1;

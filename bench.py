@@ -264,7 +264,9 @@ def run_ours(args, rank, world, local_rank):
     fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
     roofline = {"bound": "hbm", "achieved": dom["gbs"], "peak": peak, "unit": "GB/s", "frac": dom["gbs"] / peak,
                 "traffic": dom["traffic"], "traffic_source": traffic.get("source"),
-                "peak_source": peak_src, "kernel": "k_front<%d> (fused frame+FFT+filterbank+log+diff)" % dom["frame_size"],
+                "peak_source": peak_src,
+                "kernel": ("k_front<%d>" if os.environ.get("B200SPEC_PAIR", "1")[:1] == "0" else "k_front_pair<%d>") % dom["frame_size"]
+                + " (fused frame+FFT+filterbank+log+diff" + ("" if os.environ.get("B200SPEC_PAIR", "1")[:1] == "0" else ", two frames per complex FFT") + ")",
                 "kernel_ms": dom["ms"], "alg_bytes_per_launch": dom["alg_bytes"],
                 "fp32_tflops": dom["fp32_tflops"], "fp32_frac_of_74.5": dom["fp32_tflops"] / fp32_peak,
                 "note": "hop 441 makes the path FP32-issue bound (31-78 flop/B vs ridge 11); see DESIGN.md",

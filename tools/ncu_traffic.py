@@ -9,7 +9,7 @@ kn, rd, wr = hdr.index('Kernel Name'), hdr.index('dram__bytes_read.sum'), hdr.in
 scale = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
 out = {"source": sys.argv[2] if len(sys.argv) > 2 else sys.argv[1]}
 for r in rows[2:]:
-    m = re.search(r'k_front<\(?(?:int\))?(\d+)', r[kn])
+    m = re.search(r'k_front(?:_pair)?<\(?(?:int\))?(\d+)', r[kn])
     if m:
         out[m.group(1)] = float(r[rd].replace(',', '')) * scale[units[rd]] + float(r[wr].replace(',', '')) * scale[units[wr]]
 print(json.dumps(out, indent=1))
