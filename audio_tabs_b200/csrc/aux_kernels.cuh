@@ -63,27 +63,90 @@ __global__ void k_peak_reciprocal(float *__restrict__ peak, int n, float eps, fl
 }
 
 // ---- onset-strength envelope (librosa.onset.onset_strength on rows of a (T, B) matrix) ------------------
-// one block per clip: maximum of the clip's rows (power_to_db's top_db clip is relative to it)
+// maximum of each clip's rows (power_to_db's top_db clip is relative to it): grid = (kRowmaxBlocksPerClip,
+// n_clips), one warp per row at a time, block result merged with an ordered-float atomic max.
+// clip_max must hold -inf on entry (k_fill_neg_inf).
+constexpr int kRowmaxBlocksPerClip = 16;
+__global__ void k_fill_neg_inf(float *__restrict__ x, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = -INFINITY;
+}
+__device__ __forceinline__ void atomic_max_float(float *addr, float v) {
+  if (v >= 0.f) atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));          // non-negative floats order as ints
+  else atomicMin(reinterpret_cast<unsigned int *>(addr), __float_as_uint(v));          // negative ones in reverse as uints
+}
 __global__ void k_clip_rowmax(const float *__restrict__ L, long long ld_L, int B, const long long *__restrict__ frame_off,
                               float *__restrict__ clip_max) {
-  const int c = blockIdx.x;
+  const int c = blockIdx.y;
   const long long r0 = frame_off[c], rows = frame_off[c + 1] - r0;
+  const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   float m = -INFINITY;
-  for (long long i = threadIdx.x; i < rows * B; i += blockDim.x) m = fmaxf(m, L[(r0 + i / B) * ld_L + i % B]);
+  for (long long r = blockIdx.x * nw + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * nw) {
+    const float *x = L + (r0 + r) * ld_L;
+    for (int j = lane; j < B; j += 32) m = fmaxf(m, x[j]);
+  }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
   __shared__ float s_m[32];
-  if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+  if (lane == 0) s_m[threadIdx.x >> 5] = m;
   __syncthreads();
   if (threadIdx.x < 32) {
-    m = threadIdx.x < (blockDim.x >> 5) ? s_m[threadIdx.x] : -INFINITY;
+    m = threadIdx.x < nw ? s_m[threadIdx.x] : -INFINITY;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
-    if (threadIdx.x == 0) clip_max[c] = m;
+    if (threadIdx.x == 0 && rows > 0) atomic_max_float(clip_max + c, m);
   }
 }
 
-// one warp per output row; dynamic shared memory: B floats per warp (the row of positive differences)
+// Median of a row held as NPL values per lane (element e = lane * NPL + r; positions >= B hold +inf):
+// bitonic sort across the warp -- exchanges with a partner in the same lane are register swaps, the
+// others one shuffle per register -- then the two middle order statistics (np.median of an even count
+// is their mean).
+template <int NPL>
+__device__ __forceinline__ float warp_median(float (&v)[NPL], int B, int lane) {
+  constexpr int N = 32 * NPL;
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= NPL) {
+        const int lj = j / NPL;
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) {
+          const float other = __shfl_xor_sync(0xffffffffu, v[r], lj);
+          const bool asc = ((lane * NPL + r) & k) == 0;
+          const bool keep_min = ((lane & lj) == 0) == asc;
+          v[r] = keep_min ? fminf(v[r], other) : fmaxf(v[r], other);
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < NPL; ++r) {
+          if ((r & j) == 0) {
+            const bool asc = ((lane * NPL + r) & k) == 0;
+            const float lo = fminf(v[r], v[r ^ j]), hi = fmaxf(v[r], v[r ^ j]);
+            v[r] = asc ? lo : hi;
+            v[r ^ j] = asc ? hi : lo;
+          }
+        }
+      }
+    }
+  }
+  const int k_hi = B >> 1, k_lo = (B & 1) ? k_hi : k_hi - 1;
+  float a = 0.f, b = 0.f;
+#pragma unroll
+  for (int r = 0; r < NPL; ++r) {
+    if (r == k_lo % NPL) a = v[r];
+    if (r == k_hi % NPL) b = v[r];
+  }
+  a = __shfl_sync(0xffffffffu, a, k_lo / NPL);
+  b = __shfl_sync(0xffffffffu, b, k_hi / NPL);
+  return (a + b) * 0.5f;
+}
+
+// one warp per output row.  NPL > 0: the row lives in registers (NPL = values per lane, a power of two
+// with 32 * NPL >= B) and the median is a warp bitonic sort; NPL == 0: any B <= 1024, the row goes
+// through dynamic shared memory (B floats per warp) and the median is found by rank counting.
+template <int NPL>
 __global__ void k_onset_env(const float *__restrict__ L, long long ld_L, int B, const long long *__restrict__ frame_off,
                             int n_clips, long long rows, int lag, float top_db, int aggregate, int shift,
                             const float *__restrict__ clip_max, float *__restrict__ env) {
@@ -106,39 +169,61 @@ __global__ void k_onset_env(const float *__restrict__ L, long long ld_L, int B, 
     }
     const float floor_db = top_db >= 0.f ? clip_max[lo] - top_db : -INFINITY;
     const float *a = L + (r - shift) * ld_L, *b = a - (long long)lag * ld_L;
-    float sum = 0.f;
-    for (int j = lane; j < B; j += 32) {
-      const float d = fmaxf(0.f, fmaxf(a[j], floor_db) - fmaxf(b[j], floor_db));
-      row[j] = d;
-      sum += d;
-    }
     float result;
-    if (aggregate == 0) {
+    if (NPL > 0) {
+      float v[NPL > 0 ? NPL : 1];
+      float sum = 0.f;
 #pragma unroll
-      for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
-      result = sum / (float)B;
-    } else {
-      __syncwarp();
-      // rank of every element (ties broken by index); the two middle order statistics give np.median
-      const int k_hi = B >> 1, k_lo = (B & 1) ? k_hi : k_hi - 1;
-      float v_lo = 0.f, v_hi = 0.f;
-      for (int j = lane; j < B; j += 32) {
-        const float v = row[j];
-        int rank = 0;
-        for (int i = 0; i < B; ++i) {
-          const float w = row[i];
-          rank += (w < v) || (w == v && i < j);
+      for (int i = 0; i < (NPL > 0 ? NPL : 1); ++i) {
+        const int j = lane * NPL + i;
+        float d = INFINITY;                         // padding sorts to the top
+        if (j < B) {
+          d = fmaxf(0.f, fmaxf(a[j], floor_db) - fmaxf(b[j], floor_db));
+          sum += d;
         }
-        if (rank == k_lo) v_lo = v;
-        if (rank == k_hi) v_hi = v;
+        v[i] = d;
       }
+      if (aggregate == 0) {
 #pragma unroll
-      for (int d = 16; d > 0; d >>= 1) {            // exactly one lane holds each of them; the rest hold 0 (values are >= 0)
-        v_lo = fmaxf(v_lo, __shfl_xor_sync(0xffffffffu, v_lo, d));
-        v_hi = fmaxf(v_hi, __shfl_xor_sync(0xffffffffu, v_hi, d));
+        for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+        result = sum / (float)B;
+      } else {
+        result = warp_median<(NPL > 0 ? NPL : 1)>(v, B, lane);
       }
-      result = (v_lo + v_hi) * 0.5f;
-      __syncwarp();
+    } else {
+      float sum = 0.f;
+      for (int j = lane; j < B; j += 32) {
+        const float d = fmaxf(0.f, fmaxf(a[j], floor_db) - fmaxf(b[j], floor_db));
+        row[j] = d;
+        sum += d;
+      }
+      if (aggregate == 0) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+        result = sum / (float)B;
+      } else {
+        __syncwarp();
+        // rank of every element (ties broken by index); the two middle order statistics give np.median
+        const int k_hi = B >> 1, k_lo = (B & 1) ? k_hi : k_hi - 1;
+        float v_lo = 0.f, v_hi = 0.f;
+        for (int j = lane; j < B; j += 32) {
+          const float v = row[j];
+          int rank = 0;
+          for (int i = 0; i < B; ++i) {
+            const float w = row[i];
+            rank += (w < v) || (w == v && i < j);
+          }
+          if (rank == k_lo) v_lo = v;
+          if (rank == k_hi) v_hi = v;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {          // exactly one lane holds each of them; the rest hold 0 (values are >= 0)
+          v_lo = fmaxf(v_lo, __shfl_xor_sync(0xffffffffu, v_lo, d));
+          v_hi = fmaxf(v_hi, __shfl_xor_sync(0xffffffffu, v_hi, d));
+        }
+        result = (v_lo + v_hi) * 0.5f;
+        __syncwarp();
+      }
     }
     if (lane == 0) env[r] = result;
   }

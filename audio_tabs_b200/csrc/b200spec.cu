@@ -541,14 +541,21 @@ int b200spec_onset_envelope(const float *d_L, int64_t ld_L, int32_t num_bands, c
   if (aggregate != 0 && aggregate != 1) return fail(B200SPEC_ERR_ARG, "aggregate must be 0 (mean) or 1 (median)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long long *fo = reinterpret_cast<const long long *>(d_frame_off);
-  b2::k_clip_rowmax<<<n_clips, 1024, 0, st>>>(d_L, ld_L, num_bands, fo, d_clip_max);
+  b2::k_fill_neg_inf<<<(n_clips + 255) / 256, 256, 0, st>>>(d_clip_max, n_clips);
+  b2::k_clip_rowmax<<<dim3(b2::kRowmaxBlocksPerClip, (unsigned)n_clips), 256, 0, st>>>(d_L, ld_L, num_bands, fo, d_clip_max);
   CU_CHECK(cudaGetLastError());
-  g_launches++;
+  g_launches += 2;
   long long blocks = (total_frames + 7) / 8;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  const size_t smem = sizeof(float) * 8 * (size_t)num_bands;
-  b2::k_onset_env<<<(int)blocks, 256, smem, st>>>(d_L, ld_L, num_bands, fo, n_clips, total_frames, lag, top_db,
-                                                  aggregate, shift, d_clip_max, d_env);
+  // rows of up to 256 bands are sorted in registers (1, 2, 4 or 8 values per lane); wider ones go through shared memory
+  const int per_lane = (num_bands + 31) / 32;
+#define B2_ONSET_ARGS d_L, ld_L, num_bands, fo, n_clips, total_frames, lag, top_db, aggregate, shift, d_clip_max, d_env
+  if (per_lane <= 1) b2::k_onset_env<1><<<(int)blocks, 256, 0, st>>>(B2_ONSET_ARGS);
+  else if (per_lane <= 2) b2::k_onset_env<2><<<(int)blocks, 256, 0, st>>>(B2_ONSET_ARGS);
+  else if (per_lane <= 4) b2::k_onset_env<4><<<(int)blocks, 256, 0, st>>>(B2_ONSET_ARGS);
+  else if (per_lane <= 8) b2::k_onset_env<8><<<(int)blocks, 256, 0, st>>>(B2_ONSET_ARGS);
+  else b2::k_onset_env<0><<<(int)blocks, 256, sizeof(float) * 8 * (size_t)num_bands, st>>>(B2_ONSET_ARGS);
+#undef B2_ONSET_ARGS
   CU_CHECK(cudaGetLastError());
   g_launches++;
   return 0;

@@ -109,3 +109,35 @@ def test_onset_strength_batch_ragged(cuda_device):
         assert got.shape == want.shape
         assert np.abs(got - want).max() <= 5e-3 + 1e-3 * np.abs(want).max()
     assert outs[1].max() == 0.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B", [1, 7, 32, 40, 64, 91, 128, 200, 256, 300])
+@pytest.mark.parametrize("aggregate", [0, 1])
+def test_onset_envelope_kernel_any_width(cuda_device, B, aggregate):
+    """b200spec_onset_envelope on random rows: the register (bitonic sort, 1-8 values per lane) and the
+    shared-memory (rank counting, B > 256) medians, means, top_db clip, lag and shift against numpy."""
+    import torch
+    from audio_tabs_b200 import _ffi
+    rng = np.random.default_rng(100 + B)
+    lens = [37, 0, 5, 64]
+    lag, shift, top_db = 2, 3, 30.0
+    L = (rng.standard_normal((sum(lens), B)) * 20).astype(np.float32)
+    L[rng.random(L.shape) < 0.1] = 0.0                                  # ties
+    off = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+    dL, doff = torch.from_numpy(L).cuda(), torch.from_numpy(off).cuda()
+    env = torch.full((sum(lens),), -1.0, device="cuda")
+    scratch = torch.empty(len(lens), device="cuda")
+    _ffi.check(_ffi.lib().b200spec_onset_envelope(dL.data_ptr(), B, B, doff.data_ptr(), len(lens), sum(lens), lag, top_db,
+                                                  aggregate, shift, scratch.data_ptr(), env.data_ptr(), None))
+    got = env.cpu().numpy()
+    agg = np.median if aggregate else np.mean
+    for c, n in enumerate(lens):
+        S = L[off[c]:off[c + 1]]
+        want = np.zeros(n, np.float32)
+        if n:
+            S = np.maximum(S, S.max() - top_db)
+            d = agg(np.maximum(0.0, S[lag:] - S[:-lag]), axis=1) if n > lag else np.zeros(0, np.float32)
+            full = np.concatenate((np.zeros(lag + shift, np.float32), d))[:n]
+            want[:len(full)] = full
+        assert np.allclose(got[off[c]:off[c + 1]], want, rtol=1e-5, atol=1e-5), (B, aggregate, c)
