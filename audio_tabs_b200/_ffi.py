@@ -89,6 +89,8 @@ SYMBOLS = [
                                    C.c_int64, C.POINTER(OutDesc), C.c_void_p, C.c_size_t, C.c_void_p]),
     ("b200spec_clip_peak", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_int32,
                                      C.c_void_p, C.c_void_p]),
+    ("b200spec_context_stack", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int64,
+                                         C.c_int32, C.c_void_p, C.c_void_p]),
     ("b200spec_onset_envelope", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int64,
                                           C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                           C.c_void_p]),

@@ -88,9 +88,33 @@ def chord_chroma_frontend(frame_size=4096, hop_size=441.0, fps=None, num_bands=2
     return SequentialProcessor((chain, FoldedChromaProcessor(12)))
 
 
+def context_stack_device(spec, context=15, frame_off=None):
+    """DeepChromaProcessor's ``FramedSignal(frame_size=15, hop_size=1)`` + ``_dcp_flatten`` on the GPU:
+    (T, B) CUDA tensor -> (T, context*B), zero padded at both ends of every clip (``frame_off``: (n+1,)
+    int64 row offsets of the clips packed in ``spec``; default one clip)."""
+    import ctypes as C
+    import torch
+    from .. import _ffi
+    T, B = spec.shape
+    if frame_off is None:
+        frame_off = torch.tensor([0, T], dtype=torch.int64, device=spec.device)
+    out = torch.empty((T, context * B), dtype=torch.float32, device=spec.device)
+    _ffi.check(_ffi.lib().b200spec_context_stack(C.c_void_p(spec.data_ptr()), spec.stride(0), B,
+                                                 C.c_void_p(frame_off.data_ptr()), frame_off.numel() - 1, T,
+                                                 int(context), C.c_void_p(out.data_ptr()),
+                                                 C.c_void_p(torch.cuda.current_stream(spec.device).cuda_stream)))
+    return out
+
+
 def context_stack(spec, context=15):
-    """DeepChromaProcessor's ``FramedSignal(frame_size=15, hop_size=1)`` + ``_dcp_flatten``: pure data
-    movement on the host, (T, B) -> (T, context*B) with zero padding at both ends."""
+    """Host form of the same stacking (what madmom does): pure data movement, (T, B) -> (T, context*B)
+    with zero padding at both ends.  CUDA tensors go through :func:`context_stack_device`."""
+    try:
+        import torch
+        if isinstance(spec, torch.Tensor) and spec.is_cuda:
+            return context_stack_device(spec, context)
+    except ImportError:  # pragma: no cover
+        pass
     spec = np.asarray(spec)
     T, B = spec.shape
     half = context // 2

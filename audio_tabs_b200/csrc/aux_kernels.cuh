@@ -229,6 +229,28 @@ __global__ void k_onset_env(const float *__restrict__ L, long long ld_L, int B, 
   }
 }
 
+// ---- DeepChroma context stacking: out[t, c*B + j] = in[t + c - context/2, j] inside the clip, else 0 ------
+__global__ void k_context_stack(const float *__restrict__ in, long long ld_in, int B, const long long *__restrict__ frame_off,
+                                int n_clips, long long rows, int context, float *__restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int half = context / 2, W = context * B;
+  for (long long r = warp; r < rows; r += nwarps) {
+    int lo = 0, hi = n_clips;
+    while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (frame_off[mid] <= r) lo = mid; else hi = mid;
+    }
+    const long long c0 = frame_off[lo], c1 = frame_off[lo + 1];
+    float *o = out + r * (long long)W;
+    for (int i = lane; i < W; i += 32) {
+      const long long src = r + i / B - half;
+      o[i] = (src >= c0 && src < c1) ? in[src * ld_in + i % B] : 0.f;
+    }
+  }
+}
+
 // ---- stand-alone stages -------------------------------------------------------------------------
 __global__ void k_magnitude(const float2 *__restrict__ in, long long n, float *__restrict__ out) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;

@@ -530,6 +530,21 @@ int b200spec_clip_peak(const b200spec_plan *plan, const void *d_sig, const int64
   return 0;
 }
 
+int b200spec_context_stack(const float *d_in, int64_t ld_in, int32_t num_bands, const int64_t *d_frame_off,
+                           int32_t n_clips, int64_t total_frames, int32_t context, float *d_out, void *stream) {
+  if (n_clips < 0 || total_frames < 0) return fail(B200SPEC_ERR_ARG, "negative sizes");
+  if (n_clips == 0 || total_frames == 0) return 0;
+  if (!d_in || !d_frame_off || !d_out) return fail(B200SPEC_ERR_ARG, "NULL device pointer");
+  if (num_bands < 1 || ld_in < num_bands || context < 1) return fail(B200SPEC_ERR_ARG, "num_bands / ld_in / context out of range");
+  long long blocks = (total_frames + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  b2::k_context_stack<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      d_in, ld_in, num_bands, reinterpret_cast<const long long *>(d_frame_off), n_clips, total_frames, context, d_out);
+  CU_CHECK(cudaGetLastError());
+  g_launches++;
+  return 0;
+}
+
 int b200spec_onset_envelope(const float *d_L, int64_t ld_L, int32_t num_bands, const int64_t *d_frame_off,
                             int32_t n_clips, int64_t total_frames, int32_t lag, float top_db, int32_t aggregate,
                             int32_t shift, float *d_clip_max, float *d_env, void *stream) {

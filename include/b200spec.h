@@ -184,6 +184,15 @@ int b200spec_clip_peak(const b200spec_plan *plan, const void *d_sig, const int64
                        float eps, int32_t reciprocal, float *d_peak, void *stream);
 
 /*
+ * Context stacking of DeepChromaProcessor (madmom audio/chroma.py: FramedSignal(frame_size=context,
+ * hop_size=1) + _dcp_flatten; /root/reference/backend/app/services/chords/extract.py:54):
+ *   out[t, c * B + j] = in[t + c - context/2, j]  inside the clip of row t, 0 outside
+ * (T, B) -> (T, context * B), e.g. (T, 105) -> (T, 1575) for context 15.  Pure data movement.
+ */
+int b200spec_context_stack(const float *d_in, int64_t ld_in, int32_t num_bands, const int64_t *d_frame_off,
+                           int32_t n_clips, int64_t total_frames, int32_t context, float *d_out, void *stream);
+
+/*
  * Onset-strength envelope of (log-)filtered rows, librosa.onset.onset_strength semantics
  * (lag, max_size = 1, detrend = False, center shift):
  *   Lc = top_db >= 0 ? max(L, max_over_clip(L) - top_db) : L          (power_to_db top_db clip, per clip)

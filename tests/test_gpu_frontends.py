@@ -373,3 +373,19 @@ def test_device_signal_norm_through_processors(b2):
     outs = FrontEnd([log_filt_spec(2048, 441.0, 12)], device=0).process_batch([x, x * 3.0], peak_normalize=True, eps=0.0)
     assert_close(outs[0], want, what="process_batch peak_normalize")
     assert_close(outs[1], want, what="process_batch peak_normalize (gain invariance)")
+
+
+def test_context_stack_on_device(b2):
+    """DeepChroma's +-7 frame context stacking (T, 105) -> (T, 1575) as a device kernel, ragged clips."""
+    import torch
+    from audio_tabs_b200.audio.chroma import context_stack, context_stack_device
+    rng = np.random.default_rng(8)
+    lens = [40, 3, 0, 17]
+    x = rng.standard_normal((sum(lens), 105)).astype(np.float32)
+    off = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+    got = context_stack_device(torch.from_numpy(x).cuda(), 15, torch.from_numpy(off).cuda()).cpu().numpy()
+    assert got.shape == (sum(lens), 1575)
+    for c, n in enumerate(lens):
+        want = ref.dcp_context(x[off[c]:off[c + 1]], 15) if n else np.zeros((0, 1575), np.float32)
+        assert np.array_equal(got[off[c]:off[c + 1]], want)
+    assert np.array_equal(context_stack(torch.from_numpy(x[:40]).cuda(), 15).cpu().numpy(), context_stack(x[:40], 15))
