@@ -65,7 +65,7 @@ struct ResPlan {
   int power = 0;
   float log_scale = 1.f, log_floor = 0.f;
   int diff_frames = 0, positive = 0, diff_max_bins = 0;
-  int num_classes = 0;
+  int num_classes = 0, nproj = 0;
   // device tables
   float *d_window = nullptr;
   float2 *d_tw2 = nullptr, *d_tw3 = nullptr, *d_pt = nullptr, *d_wr = nullptr;
@@ -208,6 +208,8 @@ int build_res(b200spec_plan *pl, const b200spec_res_desc &d, ResPlan &r) {
     probe.fb_ns = fp.NS;
     probe.fb_ndw = (int)fp.dw.size();
     probe.diff_frames = d.diff_frames;
+    probe.num_classes = d.num_classes;
+    probe.nproj = d.num_classes > 0 ? d.proj_off[d.num_classes] : 0;
     size_t need = 0;
     switch (F) {
       case 1024: need = b2::front_smem_layout<1024>(probe, b2::MODE_LOGFILT, b2::GroupsPerCta<1024>::value); break;
@@ -239,6 +241,7 @@ int build_res(b200spec_plan *pl, const b200spec_res_desc &d, ResPlan &r) {
   if (d.num_classes > 0) {
     if (!d.proj_off || !d.proj_band || !d.proj_weight) return fail(B200SPEC_ERR_ARG, "projection arrays are NULL");
     const int np = d.proj_off[d.num_classes];
+    r.nproj = np;
     for (int i = 0; i < np; ++i)
       if (d.proj_band[i] < 0 || d.proj_band[i] >= B) return fail(B200SPEC_ERR_ARG, "proj_band out of range");
     if ((rc = upload(pl, d.proj_off, (size_t)d.num_classes + 1, &r.d_proj_off))) return rc;
@@ -495,6 +498,7 @@ int b200spec_logfilt(const b200spec_plan *plan, int32_t res, const void *d_sig, 
   p.proj = out->d_proj;
   p.ld_proj = out->ld_proj;
   p.num_classes = out->d_proj ? r.num_classes : 0;
+  p.nproj = out->d_proj ? r.nproj : 0;
   return launch_front(plan, res, b2::MODE_LOGFILT, d_sig, d_clip_off, d_frame_off, n_clips, total_frames, p,
                       d_workspace, workspace_bytes, stream);
 }

@@ -59,7 +59,7 @@ struct FrontParams {
   int power;               // 1: filterbank on |X|^2 (the magnitudes are squared as they are read)
   float log_scale, log_floor;
   int diff_frames, positive;
-  int num_classes;
+  int num_classes, nproj;   // nproj = proj_off[num_classes]
   const int *proj_off, *proj_band;
   const float *proj_w;
   // outputs (MODE_LOGFILT)
@@ -74,11 +74,16 @@ struct FrontParams {
   float *spec_out;      // (rows, N) float or float2
   int spec_complex;
   // shared-memory carve-up (byte offsets), filled by front_smem_layout()
-  int o_win, o_tw3, o_pt, o_wr, o_w4, o_band, o_dw, o_groups, group_bytes;
+  int o_win, o_tw3, o_pt, o_wr, o_w4, o_band, o_dw, o_proj, o_groups, group_bytes;
   int g_mags, g_partial, g_hist, g_lrow, g_red, g_task;  // offsets inside a group's block
   int mag_stride;                                        // floats per frame in the magnitude buffer
   int part_stride;                                       // floats per frame in the partial-sum buffer
 };
+
+// the projection (chroma fold / PCP) in CSR-by-class form, staged in shared memory: class offsets, bands, weights
+inline size_t proj_table_bytes(const FrontParams &p) {
+  return p.num_classes > 0 ? sizeof(int) * (size_t)(p.num_classes + 1) + (sizeof(int) + sizeof(float)) * (size_t)p.nproj : 0;
+}
 
 template <int F>
 inline size_t front_smem_layout(FrontParams &p, int mode, int G) {
@@ -89,12 +94,13 @@ inline size_t front_smem_layout(FrontParams &p, int mode, int G) {
   p.o_tw3 = (int)o; o = al(o + sizeof(float2) * C::TW3);
   p.o_pt = (int)o;  o = al(o + sizeof(float2) * C::PT);
   p.o_wr = (int)o;  o = al(o + sizeof(float2) * C::WR);
-  p.o_w4 = p.o_band = p.o_dw = (int)o;
+  p.o_w4 = p.o_band = p.o_dw = p.o_proj = (int)o;
   p.part_stride = p.fb_ns * kGroupThreads * 4;
   if (mode == MODE_LOGFILT) {
     p.o_w4 = (int)o;   o = al(o + (p.fb_w4_global ? 16 : sizeof(float4) * p.fb_ns * p.fb_L * kGroupThreads));
     p.o_band = (int)o; o = al(o + sizeof(int4) * (p.num_bands > 0 ? p.num_bands : 1));
     p.o_dw = (int)o;   o = al(o + sizeof(float) * (p.fb_ndw > 0 ? p.fb_ndw : 1));
+    p.o_proj = (int)o; o = al(o + proj_table_bytes(p));
   }
   p.o_groups = (int)o;
   size_t g = 0;
@@ -194,10 +200,27 @@ struct TailCtx {
   const float *s_dw;
   float *s_mags, *s_partial, *s_hist, *s_lrow, *s_red;
   int g, tid;
+  const int *s_poff, *s_pband;    // projection tables in shared memory (stage_proj)
+  const float *s_pw;
   // band-stage constants, resolved once per kernel instead of per output element
   float *out_spec, *out_diff;     // p.out + col_spec / + col_diff, or nullptr when that half is not wanted
   bool do_log, positive;
   float lmul, ladd, lfloor, lk;   // lk = log_scale * log10(2): log10(a) = lg2(a) * log10(2)
+
+  // copies the projection tables into shared memory (all threads of the CTA; the caller syncs afterwards)
+  static __device__ __forceinline__ void stage_proj(const FrontParams &p, unsigned char *smem) {
+    if (p.num_classes <= 0) return;
+    int *poff = reinterpret_cast<int *>(smem + p.o_proj);
+    int *pband = poff + p.num_classes + 1;
+    float *pw = reinterpret_cast<float *>(pband + p.nproj);
+    for (int i = threadIdx.x; i <= p.num_classes; i += blockDim.x) poff[i] = p.proj_off[i];
+    for (int i = threadIdx.x; i < p.nproj; i += blockDim.x) pband[i] = p.proj_band[i], pw[i] = p.proj_w[i];
+  }
+  __device__ __forceinline__ void resolve_proj(const FrontParams &p, const unsigned char *smem) {
+    s_poff = reinterpret_cast<const int *>(smem + p.o_proj);
+    s_pband = s_poff + p.num_classes + 1;
+    s_pw = reinterpret_cast<const float *>(s_pband + p.nproj);
+  }
 
   __device__ __forceinline__ void resolve(const FrontParams &p) {
     out_spec = (p.out != nullptr && p.col_spec >= 0) ? p.out + p.col_spec : nullptr;
@@ -328,18 +351,19 @@ __device__ __forceinline__ int front_tail(const FrontParams &p, const TailCtx &c
         }
       }
       group_bar(g);
-      for (int t = 0; t < TBF; ++t) {
+      if (p.flux != nullptr && tid < TBF) {
+        const int frame = fh + tid;
+        if (frame >= f0 && frame < f1)
+          p.flux[row0 + frame] = (s_red[tid * 4] + s_red[tid * 4 + 1]) + (s_red[tid * 4 + 2] + s_red[tid * 4 + 3]);
+      }
+      // projection: one thread per (frame, class); tables and rows in shared memory
+      for (int i = tid; i < TBF * p.num_classes; i += kGroupThreads) {
+        const int t = i / p.num_classes, cls = i - t * p.num_classes;
         const int frame = fh + t;
         if (frame < f0 || frame >= f1) continue;
-        const long long row = row0 + frame;
-        if (p.flux != nullptr && tid == 0)
-          p.flux[row] = (s_red[t * 4] + s_red[t * 4 + 1]) + (s_red[t * 4 + 2] + s_red[t * 4 + 3]);
-        if (tid < p.num_classes) {
-          float acc = 0.f;
-          for (int i = p.proj_off[tid]; i < p.proj_off[tid + 1]; ++i)
-            acc = fmaf(__ldg(&p.proj_w[i]), s_lrow[t * B + __ldg(&p.proj_band[i])], acc);
-          p.proj[row * p.ld_proj + tid] = acc;
-        }
+        float acc = 0.f;
+        for (int k = c.s_poff[cls]; k < c.s_poff[cls + 1]; ++k) acc = fmaf(c.s_pw[k], s_lrow[t * B + c.s_pband[k]], acc);
+        p.proj[(row0 + frame) * p.ld_proj + cls] = acc;
       }
     }
   }
@@ -369,6 +393,7 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
       for (int i = threadIdx.x; i < p.fb_ns * p.fb_L * kGroupThreads; i += blockDim.x) s_w4[i] = p.fb_w4[i];
     for (int i = threadIdx.x; i < p.num_bands; i += blockDim.x) s_band[i] = p.fb_band[i];
     for (int i = threadIdx.x; i < p.fb_ndw; i += blockDim.x) s_dw[i] = p.fb_dw[i];
+    TailCtx::stage_proj(p, smem);
     // magnitudes (and their padding, which zero-weight taps may read) start out finite
     float *allmags = reinterpret_cast<float *>(smem + p.o_groups);
     for (int gi = 0; gi < G; ++gi)
@@ -398,6 +423,7 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
   volatile int *s_task = reinterpret_cast<volatile int *>(gmem + p.g_task);
   TailCtx tctx{s_w4, s_band, s_dw, s_mags, s_partial, s_hist, s_lrow, s_red, g, tid};
   tctx.resolve(p);
+  tctx.resolve_proj(p, smem);
 
   // per-thread constants ---------------------------------------------------------------------
   float2 tw2r[16];                       // pass-2 twiddles of this thread's k1

@@ -53,6 +53,7 @@ inline size_t pair_smem_layout(FrontParams &p, int G) {
   p.o_w4 = (int)o;   o = al(o + (p.fb_w4_global ? 16 : sizeof(float4) * p.fb_ns * p.fb_L * kGroupThreads));
   p.o_band = (int)o; o = al(o + sizeof(int4) * (p.num_bands > 0 ? p.num_bands : 1));
   p.o_dw = (int)o;   o = al(o + sizeof(float) * (p.fb_ndw > 0 ? p.fb_ndw : 1));
+  p.o_proj = (int)o; o = al(o + proj_table_bytes(p));
   p.o_groups = (int)o;
   size_t g = 0;
   g = al(g + sizeof(float2) * P::PPS * C2::BUF);   // in-place FFT buffers (one per pair)
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front_pair(const FrontP
     for (int i = threadIdx.x; i < p.fb_ns * p.fb_L * kGroupThreads; i += blockDim.x) s_w4[i] = p.fb_w4[i];
   for (int i = threadIdx.x; i < p.num_bands; i += blockDim.x) s_band[i] = p.fb_band[i];
   for (int i = threadIdx.x; i < p.fb_ndw; i += blockDim.x) s_dw[i] = p.fb_dw[i];
+  TailCtx::stage_proj(p, smem);
   for (int gi = 0; gi < G; ++gi)      // magnitudes (and their padding, which zero-weight taps may read) start out finite
     for (int i = threadIdx.x; i < (P::INPLACE ? 2 * C2::BUF : TB * MS); i += blockDim.x)
       reinterpret_cast<float *>(smem + p.o_groups + (size_t)gi * p.group_bytes + p.g_mags)[i] = 0.f;
@@ -106,6 +108,7 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front_pair(const FrontP
                reinterpret_cast<float *>(gmem + p.g_hist), reinterpret_cast<float *>(gmem + p.g_lrow),
                reinterpret_cast<float *>(gmem + p.g_red), g, tid};
   tctx.resolve(p);
+  tctx.resolve_proj(p, smem);
 
   // per-thread constants ---------------------------------------------------------------------
   float2 tw2r[16];                       // pass-2 twiddles of this thread's k1
