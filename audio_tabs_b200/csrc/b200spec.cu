@@ -209,6 +209,7 @@ int build_res(b200spec_plan *pl, const b200spec_res_desc &d, ResPlan &r) {
     probe.fb_ndw = (int)fp.dw.size();
     probe.diff_frames = d.diff_frames;
     probe.num_classes = d.num_classes;
+    probe.mag_cap = (kmax + 16 + 3) & ~3;
     probe.nproj = d.num_classes > 0 ? d.proj_off[d.num_classes] : 0;
     size_t need = 0;
     switch (F) {
@@ -265,7 +266,7 @@ int carve_workspace(void *ws, size_t bytes, int n_clips, Workspace &w) {
 }
 
 int choose_chunk(const b200spec_plan *pl, int F, long long total_frames, int kd) {
-  const int G = (F == 8192) ? 2 : 4;
+  const int G = (F == 8192) ? 3 : 4;
   const long long slots = (long long)pl->num_sms * G;
   long long chunk = total_frames / (slots * 8);
   const int lo = kd > 0 ? 16 : 4;
@@ -325,6 +326,7 @@ int launch_front(const b200spec_plan *pl, int res, int mode, const void *d_sig, 
   p.fb_kmin = r.fb_kmin;
   p.fb_ndw = r.fb_ndw;
   p.fb_w4_global = r.fb_w4_global;
+  p.mag_cap = (r.kmax + 16 + 3) & ~3;   // k_front<8192> keeps only the magnitude bins the filterbank reads (+ one slab of slack)
   p.num_bands = r.num_bands;
   p.nnz = r.nnz;
   p.kmax = r.kmax;

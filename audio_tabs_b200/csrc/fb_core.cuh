@@ -59,12 +59,12 @@ struct MagInPlace {
 // W4G: the weight table did not fit in shared memory and is read from global memory (read-only path).
 // POW: the filterbank works on the power spectrum: every magnitude is squared as it is read.
 template <int L, int TBF, class MA, bool W4G = false, bool POW = false>
-B2_HD void fb_slabs(const float4 *s_w4, const float *s_mags, float *s_part, int ns, int kmin, int pstride, int tid) {
-  constexpr int MS = MA::MS;
+B2_HD void fb_slabs(const float4 *s_w4, const float *s_mags, float *s_part, int ns, int kmin, int pstride, int tid,
+                    int cap = MA::MS) {   // cap: floats of a magnitude row that exist (<= MS)
   for (int s = 0; s < ns; ++s) {
     const int g = s * kGroupThreads + tid;
     int k0 = kmin + g * L;
-    if (k0 > MS - L) k0 = MS - L;                // slabs past the spectrum carry zero weights
+    if (k0 > cap - L) k0 = cap - L;              // slabs past the kept spectrum carry zero weights
     const float4 *wp = s_w4 + s * L * kGroupThreads + tid;
     float4 acc[TBF];
 #pragma unroll
@@ -95,15 +95,15 @@ B2_HD void fb_slabs(const float4 *s_w4, const float *s_mags, float *s_part, int 
 
 template <int TBF, class MA, bool POW = false>
 B2_HD void fb_slabs_dispatch(int L, const float4 *s_w4, const float *s_mags, float *s_part, int ns, int kmin,
-                             int pstride, int tid) {
+                             int pstride, int tid, int cap = MA::MS) {
   switch (L) {
-    case 3: fb_slabs<3, TBF, MA, false, POW>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
-    case 5: fb_slabs<5, TBF, MA, false, POW>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
-    case 7: fb_slabs<7, TBF, MA, false, POW>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
-    case 9: fb_slabs<9, TBF, MA, false, POW>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
-    case 11: fb_slabs<11, TBF, MA, false, POW>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
-    case 13: fb_slabs<13, TBF, MA, false, POW>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
-    default: fb_slabs<15, TBF, MA, false, POW>(s_w4, s_mags, s_part, ns, kmin, pstride, tid); break;
+    case 3: fb_slabs<3, TBF, MA, false, POW>(s_w4, s_mags, s_part, ns, kmin, pstride, tid, cap); break;
+    case 5: fb_slabs<5, TBF, MA, false, POW>(s_w4, s_mags, s_part, ns, kmin, pstride, tid, cap); break;
+    case 7: fb_slabs<7, TBF, MA, false, POW>(s_w4, s_mags, s_part, ns, kmin, pstride, tid, cap); break;
+    case 9: fb_slabs<9, TBF, MA, false, POW>(s_w4, s_mags, s_part, ns, kmin, pstride, tid, cap); break;
+    case 11: fb_slabs<11, TBF, MA, false, POW>(s_w4, s_mags, s_part, ns, kmin, pstride, tid, cap); break;
+    case 13: fb_slabs<13, TBF, MA, false, POW>(s_w4, s_mags, s_part, ns, kmin, pstride, tid, cap); break;
+    default: fb_slabs<15, TBF, MA, false, POW>(s_w4, s_mags, s_part, ns, kmin, pstride, tid, cap); break;
   }
 }
 

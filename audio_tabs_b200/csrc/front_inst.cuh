@@ -12,7 +12,8 @@ struct GroupsPerCta {
 #ifndef B2_GROUPS
 #define B2_GROUPS 4
 #endif
-  static constexpr int value = (F == 8192) ? 2 : B2_GROUPS;
+  static constexpr int value = (F == 8192) ? 3 : B2_GROUPS;       // 8192: three groups when the magnitude rows are
+  static constexpr int fallback = (F == 8192) ? 2 : B2_GROUPS;    // short (band-limited filterbank), else two
 };
 
 constexpr size_t kMaxSmemPerCta = 227 * 1024;   // opt-in dynamic shared memory per CTA on sm_100
@@ -22,9 +23,8 @@ struct LaunchResult {
   int launches;
 };
 
-template <int F, int IN, int MODE>
-static cudaError_t launch_one(FrontParams &p, int num_sms, long long task_bound, cudaStream_t st) {
-  constexpr int G = GroupsPerCta<F>::value;
+template <int F, int IN, int MODE, int G>
+static cudaError_t launch_one_g(FrontParams &p, int num_sms, long long task_bound, cudaStream_t st) {
   const size_t smem = front_smem_layout<F>(p, MODE, G);
   if (smem > kMaxSmemPerCta) return cudaErrorInvalidConfiguration;   // reported as "unsupported" by the caller
   auto kern = k_front<F, IN, MODE, G>;
@@ -35,6 +35,14 @@ static cudaError_t launch_one(FrontParams &p, int num_sms, long long task_bound,
   int grid = (int)(ctas < num_sms ? (ctas < 1 ? 1 : ctas) : num_sms);
   kern<<<grid, kGroupThreads * G, smem, st>>>(p);
   return cudaGetLastError();
+}
+
+template <int F, int IN, int MODE>
+static cudaError_t launch_one(FrontParams &p, int num_sms, long long task_bound, cudaStream_t st) {
+  cudaError_t e = launch_one_g<F, IN, MODE, GroupsPerCta<F>::value>(p, num_sms, task_bound, st);
+  if (e == cudaErrorInvalidConfiguration && GroupsPerCta<F>::fallback != GroupsPerCta<F>::value)
+    e = launch_one_g<F, IN, MODE, GroupsPerCta<F>::fallback>(p, num_sms, task_bound, st);
+  return e;
 }
 
 template <int F>

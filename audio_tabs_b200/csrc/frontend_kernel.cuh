@@ -77,6 +77,7 @@ struct FrontParams {
   int o_win, o_tw3, o_pt, o_wr, o_w4, o_band, o_dw, o_proj, o_groups, group_bytes;
   int g_mags, g_partial, g_hist, g_lrow, g_red, g_task;  // offsets inside a group's block
   int mag_stride;                                        // floats per frame in the magnitude buffer
+  int mag_cap;                                           // floats of a magnitude row that are kept (k_front<8192>: kmax + slack)
   int part_stride;                                       // floats per frame in the partial-sum buffer
 };
 
@@ -108,7 +109,8 @@ inline size_t front_smem_layout(FrontParams &p, int mode, int G) {
   p.g_mags = p.g_partial = p.g_hist = p.g_lrow = (int)g;
   p.mag_stride = C::MS;
   if (mode == MODE_LOGFILT) {
-    p.g_mags = (int)g;    g = al(g + sizeof(float) * C::TB * p.mag_stride);
+    if (p.mag_cap <= 0 || p.mag_cap > C::MS || C::TB > 1) p.mag_cap = C::MS;   // rows are MS apart when a batch holds several
+    p.g_mags = (int)g;    g = al(g + sizeof(float) * (C::TB > 1 ? C::TB * p.mag_stride : p.mag_cap));
     p.g_partial = (int)g; g = al(g + sizeof(float) * C::TBF * p.part_stride);
     p.g_hist = (int)g;    g = al(g + sizeof(float) * (p.diff_frames > 0 ? p.diff_frames : 1) * p.num_bands);
     p.g_lrow = (int)g;    g = al(g + sizeof(float) * C::TBF * p.num_bands);
@@ -200,6 +202,7 @@ struct TailCtx {
   const float *s_dw;
   float *s_mags, *s_partial, *s_hist, *s_lrow, *s_red;
   int g, tid;
+  int mag_cap;                    // floats of a magnitude row that exist (0: all MS of them)
   const int *s_poff, *s_pband;    // projection tables in shared memory (stage_proj)
   const float *s_pw;
   // band-stage constants, resolved once per kernel instead of per output element
@@ -244,6 +247,7 @@ __device__ __forceinline__ int front_tail(const FrontParams &p, const TailCtx &c
   const int g = c.g, tid = c.tid;
   const int B = p.num_bands, kd = p.diff_frames, pstride = p.part_stride;
   constexpr int MS = MA::MS;
+  const int cap = c.mag_cap > 0 ? c.mag_cap : MS;
 #pragma unroll 1
   for (int h = 0; h < TB; h += TBF) {
     const int fh = fb + h;
@@ -252,12 +256,12 @@ __device__ __forceinline__ int front_tail(const FrontParams &p, const TailCtx &c
     const float *hmags = s_mags + h * MS;
     // ---- K2a: slab filterbank ----
     if (p.fb_w4_global) {
-      if (p.power) fb_slabs<15, TBF, MA, true, true>(p.fb_w4, hmags, s_partial, p.fb_ns, p.fb_kmin, pstride, tid);
-      else fb_slabs<15, TBF, MA, true, false>(p.fb_w4, hmags, s_partial, p.fb_ns, p.fb_kmin, pstride, tid);
+      if (p.power) fb_slabs<15, TBF, MA, true, true>(p.fb_w4, hmags, s_partial, p.fb_ns, p.fb_kmin, pstride, tid, cap);
+      else fb_slabs<15, TBF, MA, true, false>(p.fb_w4, hmags, s_partial, p.fb_ns, p.fb_kmin, pstride, tid, cap);
     } else if (p.power) {
-      fb_slabs_dispatch<TBF, MA, true>(p.fb_L, s_w4, hmags, s_partial, p.fb_ns, p.fb_kmin, pstride, tid);
+      fb_slabs_dispatch<TBF, MA, true>(p.fb_L, s_w4, hmags, s_partial, p.fb_ns, p.fb_kmin, pstride, tid, cap);
     } else {
-      fb_slabs_dispatch<TBF, MA, false>(p.fb_L, s_w4, hmags, s_partial, p.fb_ns, p.fb_kmin, pstride, tid);
+      fb_slabs_dispatch<TBF, MA, false>(p.fb_L, s_w4, hmags, s_partial, p.fb_ns, p.fb_kmin, pstride, tid, cap);
     }
     group_bar(g);
     // ---- K2b/K3: band sum, log10, lagged difference, stacked store ----
@@ -397,7 +401,7 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
     // magnitudes (and their padding, which zero-weight taps may read) start out finite
     float *allmags = reinterpret_cast<float *>(smem + p.o_groups);
     for (int gi = 0; gi < G; ++gi)
-      for (int i = threadIdx.x; i < TB * MS; i += blockDim.x)
+      for (int i = threadIdx.x; i < (TB > 1 ? TB * MS : p.mag_cap); i += blockDim.x)
         reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(allmags) + (size_t)gi * p.group_bytes + p.g_mags)[i] = 0.f;
   }
   __syncthreads();
@@ -424,6 +428,8 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
   TailCtx tctx{s_w4, s_band, s_dw, s_mags, s_partial, s_hist, s_lrow, s_red, g, tid};
   tctx.resolve(p);
   tctx.resolve_proj(p, smem);
+  tctx.mag_cap = p.mag_cap;
+  const int kcap = p.mag_cap;            // magnitude bins >= kcap feed no band: neither formed nor stored (frame 8192)
 
   // per-thread constants ---------------------------------------------------------------------
   float2 tw2r[16];                       // pass-2 twiddles of this thread's k1
@@ -526,11 +532,11 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
             float *mags = s_mags + (sub + fl) * MS;
             if (u != 0)
               fft_pass3_unit<F>(u, fbuf + pa_off, fbuf + pb_off, s_tw3 + u, s_pt + u,
-                                [&](int k, float2 X) { mags[k] = cabs_fast(X); });
+                                [&](int k, float2 X) { if (TB > 1 || k < kcap) mags[k] = cabs_fast(X); });
             if (tid < 2 * R3) {   // the two self-paired columns: one bin per lane of warp 0
               int bin;
               const float2 X = fft_pass3_selfpaired<F>(tid, fbuf, s_wr, s_pt, bin);
-              mags[bin] = cabs_fast(X);
+              if (TB > 1 || bin < kcap) mags[bin] = cabs_fast(X);
             }
           } else if (frame >= f0) {
             const long long row = row0 + frame;
