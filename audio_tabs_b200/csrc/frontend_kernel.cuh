@@ -203,8 +203,6 @@ struct TailCtx {
   float *s_mags, *s_partial, *s_hist, *s_lrow, *s_red;
   int g, tid;
   int mag_cap;                    // floats of a magnitude row that exist (0: all MS of them)
-  const int *s_poff, *s_pband;    // projection tables in shared memory (stage_proj)
-  const float *s_pw;
   // band-stage constants, resolved once per kernel instead of per output element
   float *out_spec, *out_diff;     // p.out + col_spec / + col_diff, or nullptr when that half is not wanted
   bool do_log, positive;
@@ -219,12 +217,6 @@ struct TailCtx {
     for (int i = threadIdx.x; i <= p.num_classes; i += blockDim.x) poff[i] = p.proj_off[i];
     for (int i = threadIdx.x; i < p.nproj; i += blockDim.x) pband[i] = p.proj_band[i], pw[i] = p.proj_w[i];
   }
-  __device__ __forceinline__ void resolve_proj(const FrontParams &p, const unsigned char *smem) {
-    s_poff = reinterpret_cast<const int *>(smem + p.o_proj);
-    s_pband = s_poff + p.num_classes + 1;
-    s_pw = reinterpret_cast<const float *>(s_pband + p.nproj);
-  }
-
   __device__ __forceinline__ void resolve(const FrontParams &p) {
     out_spec = (p.out != nullptr && p.col_spec >= 0) ? p.out + p.col_spec : nullptr;
     out_diff = (p.out != nullptr && p.col_diff >= 0) ? p.out + p.col_diff : nullptr;
@@ -360,13 +352,17 @@ __device__ __forceinline__ int front_tail(const FrontParams &p, const TailCtx &c
         if (frame >= f0 && frame < f1)
           p.flux[row0 + frame] = (s_red[tid * 4] + s_red[tid * 4 + 1]) + (s_red[tid * 4 + 2] + s_red[tid * 4 + 3]);
       }
-      // projection: one thread per (frame, class); tables and rows in shared memory
+      // projection: one thread per (frame, class); tables (stage_proj) and rows in shared memory
+      extern __shared__ __align__(16) unsigned char smem_base[];
+      const int *s_poff = reinterpret_cast<const int *>(smem_base + p.o_proj);
+      const int *s_pband = s_poff + p.num_classes + 1;
+      const float *s_pw = reinterpret_cast<const float *>(s_pband + p.nproj);
       for (int i = tid; i < TBF * p.num_classes; i += kGroupThreads) {
         const int t = i / p.num_classes, cls = i - t * p.num_classes;
         const int frame = fh + t;
         if (frame < f0 || frame >= f1) continue;
         float acc = 0.f;
-        for (int k = c.s_poff[cls]; k < c.s_poff[cls + 1]; ++k) acc = fmaf(c.s_pw[k], s_lrow[t * B + c.s_pband[k]], acc);
+        for (int k = s_poff[cls]; k < s_poff[cls + 1]; ++k) acc = fmaf(s_pw[k], s_lrow[t * B + s_pband[k]], acc);
         p.proj[(row0 + frame) * p.ld_proj + cls] = acc;
       }
     }
@@ -427,7 +423,6 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
   volatile int *s_task = reinterpret_cast<volatile int *>(gmem + p.g_task);
   TailCtx tctx{s_w4, s_band, s_dw, s_mags, s_partial, s_hist, s_lrow, s_red, g, tid};
   tctx.resolve(p);
-  tctx.resolve_proj(p, smem);
   tctx.mag_cap = p.mag_cap;
   const int kcap = p.mag_cap;            // magnitude bins >= kcap feed no band: neither formed nor stored (frame 8192)
 

@@ -108,7 +108,6 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front_pair(const FrontP
                reinterpret_cast<float *>(gmem + p.g_hist), reinterpret_cast<float *>(gmem + p.g_lrow),
                reinterpret_cast<float *>(gmem + p.g_red), g, tid};
   tctx.resolve(p);
-  tctx.resolve_proj(p, smem);
 
   // per-thread constants ---------------------------------------------------------------------
   float2 tw2r[16];                       // pass-2 twiddles of this thread's k1
