@@ -389,3 +389,31 @@ def test_context_stack_on_device(b2):
         want = ref.dcp_context(x[off[c]:off[c + 1]], 15) if n else np.zeros((0, 1575), np.float32)
         assert np.array_equal(got[off[c]:off[c + 1]], want)
     assert np.array_equal(context_stack(torch.from_numpy(x[:40]).cuda(), 15).cpu().numpy(), context_stack(x[:40], 15))
+
+
+def test_repeated_runs_are_bitwise_identical(b2):
+    """No atomics or ordering-dependent sums on the data path: the same packed batch gives the same bits
+    every time (a shared-memory race between the phases of a group would show up here first; the pool
+    has compute-sanitizer closed).  64 clips of different length keep all 148 x 4 groups busy and exercise
+    the dynamic task queue in different interleavings."""
+    import torch
+    from audio_tabs_b200.frontends import beat_specs
+    from audio_tabs_b200.plan import FrontEnd
+    from audio_tabs_b200.synth import synth_batch_device
+    dev = torch.device("cuda", 0)
+    n = 44100 * 20
+    sig = synth_batch_device(64, n, seed=99, device=dev).reshape(-1)
+    lens = [n - 1000 * (i % 7) for i in range(64)]
+    clips = [sig[i * n:i * n + lens[i]] for i in range(64)]
+    fe = FrontEnd(beat_specs(), device=0)
+    packed = fe.pack(clips)
+    first = fe.run_packed(packed).clone()
+    assert torch.isfinite(first).all()
+    for _ in range(4):
+        assert torch.equal(fe.run_packed(packed), first)
+    flux = [torch.empty(packed.total_frames, device=dev) for _ in fe.specs]
+    again = fe.run_packed(packed, flux=flux)
+    assert torch.equal(again, first)
+    B = fe.specs[2].num_bands
+    c = fe.col[2]
+    assert torch.allclose(flux[2], first[:, c + B:c + 2 * B].sum(dim=1), rtol=1e-5, atol=1e-5)
