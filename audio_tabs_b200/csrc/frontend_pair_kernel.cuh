@@ -35,6 +35,19 @@ struct PairCfg {
   static constexpr bool INPLACE = false;
 #endif
   using MA = typename std::conditional<INPLACE, MagInPlace<2 * F, MS>, MagLinear<MS>>::type;
+  // TMA staging: once pass 3 has consumed the FFT buffer, one thread starts a bulk copy (cp.async.bulk,
+  // completion on an mbarrier) of the raw samples the FIRST step of the next tail batch needs into that
+  // buffer; it lands while the filterbank / band stage runs, and pass 1 then reads shared memory instead
+  // of waiting for L2.  float32 mono only (the copy is byte-wise); the span of all FPS frames of a step
+  // must fit the PPS * BUF complex slots of the buffer.  Measured on B200 (config 2): frame 4096 unchanged
+  // (7.14 ms with and without: the other groups already cover the L2 latency), frames 1024 / 2048 5 % / 4 %
+  // slower (the extra barrier between reading the raw samples and overwriting them), so it is compiled in
+  // only with -DB2_PAIR_TMA.
+#ifdef B2_PAIR_TMA
+  static constexpr bool TMA = true;
+#else
+  static constexpr bool TMA = false;
+#endif
   static_assert(TB % FPS == 0, "tail batch must hold whole FFT steps");
   static_assert(!INPLACE || (TB == FPS && PPS == 1), "in-place magnitudes: one pair per tail batch");
 };
@@ -123,6 +136,17 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front_pair(const FrontP
 
   const int total_tasks = p.task_off[p.n_clips];
   const int kd = p.diff_frames;
+  constexpr bool kTma = P::TMA && (IN == IN_F32_MONO);
+  const long long sig_bytes = kTma ? p.clip_off[p.n_clips] * 4 : 0;      // the packed buffer holds at least all clips
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(gmem + p.g_task + 8);   // one mbarrier per group
+  uint32_t bar_parity = 0;
+  bool staged = false;                   // the samples of the next step's frames are on their way into buf
+  int st_delta = 0;                      // offset (floats) of the first frame's first sample inside buf
+  long long st_s0 = 0;                   // sample index (in the clip) of that first sample
+  if (kTma) {
+    if (tid == 0) mbar_init(s_bar, 1);
+    group_bar(g);
+  }
 
   for (;;) {
     if (tid == 0) *s_task = atomicAdd(p.task_counter, 1);
@@ -148,6 +172,7 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front_pair(const FrontP
     const float cscale = p.clip_scale != nullptr ? __ldg(p.clip_scale + c) : 1.f;
 
     int hslot = kd > 0 ? fs % kd : 0;                        // difference ring slot of frame fb
+    staged = false;                                          // (a task never ends with a copy in flight: fn + FPS <= f1)
     for (int fb = fs; fb < f1; fb += TB) {
       // =============== FFT of the TB frames of this tail batch, FPS frames (PPS pairs) per step ===============
 #pragma unroll 1
@@ -161,6 +186,30 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front_pair(const FrontP
           const long long sB = (long long)((double)(fA + 1) * p.hop) - (F / 2) - p.origin;
           const bool hasB = fA + 1 < f1;
           const bool interior = (sA >= 0) && (sB + F <= nsamp) && hasB;     // sB >= sA
+          if (kTma && staged && sub == 0) {
+            // raw samples are in buf (TMA): take this thread's elements into registers, let the whole group
+            // finish reading, then transform and overwrite the buffer
+            mbar_wait(s_bar, bar_parity);
+            const float *raw = reinterpret_cast<const float *>(buf) + st_delta;
+            const float *ra = raw + (int)(sA - st_s0) + b12, *rb = raw + (int)(sB - st_s0) + b12;
+            float xa[16 * C2::IT12], xb[16 * C2::IT12];
+#pragma unroll
+            for (int it = 0; it < C2::IT12; ++it)
+#pragma unroll
+              for (int n1 = 0; n1 < 16; ++n1) {
+                xa[it * 16 + n1] = ra[it * kGroupThreads + n1 * C2::BPF];
+                xb[it * 16 + n1] = rb[it * kGroupThreads + n1 * C2::BPF];
+              }
+            group_bar(g);
+#pragma unroll
+            for (int it = 0; it < C2::IT12; ++it) {
+              const float *wp = w1 + it * kGroupThreads;
+              fft_pass1<F2>([&](int n1) {
+                const float w = wp[n1 * C2::BPF];
+                return make_float2(w * xa[it * 16 + n1], w * xb[it * 16 + n1]);
+              }, p1 + it * kGroupThreads);
+            }
+          } else
 #pragma unroll 1
           for (int it = 0; it < C2::IT12; ++it) {
             const int b = b12 + it * kGroupThreads;
@@ -225,7 +274,30 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front_pair(const FrontP
         }
         group_bar(g);   // pass-3 reads done before the next pass 1 overwrites buf; magnitudes visible
       }
-      // =============== tail for the TB frames of this batch ===============
+      // =============== stage the next batch's first step (TMA), then the tail of this batch ===============
+      if (kTma) {
+        if (staged) bar_parity ^= 1;                         // the wait of this batch's first step is done
+        staged = false;
+        const int fn = fb + TB;                              // first frame of the next batch
+        if (fn + FPS <= f1) {
+          const long long s_first = (long long)((double)fn * p.hop) - (F / 2) - p.origin;
+          const long long s_last = (long long)((double)(fn + FPS - 1) * p.hop) - (F / 2) - p.origin;
+          const long long g0 = samp0 + s_first;              // index in the packed buffer
+          const int delta = (int)(g0 & 3);                   // the bulk copy starts on a 16-byte boundary
+          const long long bytes = ((s_last - s_first + F + delta + 3) & ~3LL) * 4;
+          if (s_first >= 0 && s_last + F <= nsamp && bytes <= (long long)sizeof(float2) * PPS * C2::BUF &&
+              (g0 - delta) * 4 + bytes <= sig_bytes && ((reinterpret_cast<uintptr_t>(p.sig) & 15) == 0)) {
+            staged = true;
+            st_delta = delta;
+            st_s0 = s_first;
+            if (tid == 0) {
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic accesses to buf are done (barrier)
+              mbar_expect_tx(s_bar, (uint32_t)bytes);
+              tma_load_1d(buf, reinterpret_cast<const float *>(p.sig) + (g0 - delta), (uint32_t)bytes, s_bar);
+            }
+          }
+        }
+      }
       hslot = front_tail<TB, TBF, typename P::MA>(p, tctx, fb, f0, f1, row0, hslot, cscale);
       if (P::INPLACE) group_bar(g);   // the band stage has read its magnitudes before pass 1 overwrites the buffer
     }
