@@ -22,7 +22,11 @@ struct PairCfg {
   static constexpr int PPS = C2::FPG;             // pairs per group step
   static constexpr int FPS = 2 * PPS;             // frames per group step
   static constexpr int TB = FftCfg<F>::TB >= FPS ? FftCfg<F>::TB : FPS;   // frames per tail batch (multiple of FPS)
+#ifdef B2_PAIR_TBF_2048   // tuning override: frames per filterbank / band-stage call at frame 2048
+  static constexpr int TBF = (F == 2048) ? B2_PAIR_TBF_2048 : (TB < 4 ? TB : 4);
+#else
   static constexpr int TBF = TB < 4 ? TB : 4;
+#endif
   static constexpr int MS = FftCfg<F>::MS;        // floats per frame in the magnitude buffer
   // Frame 4096: a 33 KB FFT buffer per pair plus 16 KB of magnitudes allow three groups per SM only.
   // -DB2_PAIR_INPLACE makes pass 3 write the magnitudes IN PLACE of the columns it has consumed
