@@ -169,22 +169,48 @@ def load_traffic():
         return {}
 
 
-def pcie_bandwidth(dev, nbytes=1 << 30):
-    """GB/s of one large pinned H2D and D2H copy (explains the e2e bound)."""
+def pcie_bandwidth(dev, in_bytes, out_bytes):
+    """What the host <-> device link allows for one step (explains the e2e bound): GB/s of a pinned H2D copy of
+    the step's input and a D2H copy of its output, each alone and both at once (the pipeline overlaps them,
+    and the two directions slow each other down by ~10 %)."""
     import torch
-    h = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
-    d = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    res = {}
-    for name, (dst, src) in (("h2d_gbs", (d, h)), ("d2h_gbs", (h, d))):
-        dst.copy_(src, non_blocking=True)
+    hi = torch.empty(in_bytes, dtype=torch.uint8, pin_memory=True)
+    ho = torch.empty(out_bytes, dtype=torch.uint8, pin_memory=True)
+    di = torch.empty(in_bytes, dtype=torch.uint8, device=dev)
+    do = torch.empty(out_bytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def timed(fn):
+        fn()
         torch.cuda.synchronize(dev)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        dst.copy_(src, non_blocking=True)
+        fn()
         b.record()
         torch.cuda.synchronize(dev)
-        res[name] = nbytes / a.elapsed_time(b) / 1e6
-    return res
+        return a.elapsed_time(b)
+
+    def both():
+        cur = torch.cuda.current_stream(dev)
+        e = torch.cuda.Event()
+        e.record(cur)
+        s1.wait_event(e)
+        s2.wait_event(e)
+        with torch.cuda.stream(s1):
+            di.copy_(hi, non_blocking=True)
+            e1 = torch.cuda.Event()
+            e1.record(s1)
+        with torch.cuda.stream(s2):
+            ho.copy_(do, non_blocking=True)
+            e2 = torch.cuda.Event()
+            e2.record(s2)
+        cur.wait_event(e1)
+        cur.wait_event(e2)
+
+    ms_h2d = timed(lambda: di.copy_(hi, non_blocking=True))
+    ms_d2h = timed(lambda: ho.copy_(do, non_blocking=True))
+    ms_both = timed(both)
+    return {"h2d_gbs": in_bytes / ms_h2d / 1e6, "d2h_gbs": out_bytes / ms_d2h / 1e6, "both_directions_ms": ms_both}
 
 
 def run_ours(args, rank, world, local_rank):
@@ -302,10 +328,10 @@ def run_ours(args, rank, world, local_rank):
                "api": "audio_tabs_b200.plan.FrontEnd.process_batch_pinned", "numa_bound_cpus": len(numa_cpus)}
         del host_in, host_out
         if rank == 0:
-            pc = pcie_bandwidth(dev)
+            pc = pcie_bandwidth(dev, int(in_bytes), int(out_bytes))
             e2e["pcie"] = pc
-            # both directions overlap: the slower copy bounds the step
-            e2e["pcie_bound_value"] = world * audio_seconds / max(in_bytes / pc["h2d_gbs"], out_bytes / pc["d2h_gbs"]) * 1e9
+            # the step cannot be faster than moving its input in and its output out at the same time
+            e2e["pcie_bound_value"] = world * audio_seconds / (pc["both_directions_ms"] * 1e-3)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
