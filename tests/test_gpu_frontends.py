@@ -417,3 +417,37 @@ def test_repeated_runs_are_bitwise_identical(b2):
     B = fe.specs[2].num_bands
     c = fe.col[2]
     assert torch.allclose(flux[2], first[:, c + B:c + 2 * B].sum(dim=1), rtol=1e-5, atol=1e-5)
+
+
+def test_full_config2_batch_properties(b2):
+    """BASELINE configs[1] at its FULL size (64 stems x 180 s -> (1 152 000, 314)): every clip's rows agree
+    with running that clip alone (different task sizes / frame pairings: float32 rounding only), the tail
+    of the last clip (right zero padding) and the head of the first match the oracle, nothing leaks
+    across clip boundaries, all values finite and non-negative."""
+    import torch
+    from audio_tabs_b200.frontends import beat_specs
+    from audio_tabs_b200.plan import FrontEnd, Packed
+    from audio_tabs_b200.synth import synth_batch_device
+    n, nc = 180 * SR, 64
+    dev = torch.device("cuda", 0)
+    sig = synth_batch_device(nc, n, seed=2000, device=dev)
+    fe = FrontEnd(beat_specs(), device=0)
+    packed = Packed(sig, [n] * nc, 441.0)
+    out = fe.run_packed(packed)
+    assert out.shape == (nc * 18000, 314)
+    assert bool(torch.isfinite(out).all()) and bool((out >= 0).all())
+    for c in (0, 31, 63):
+        alone = fe.run_packed(Packed(sig[c * n:(c + 1) * n], [n], 441.0))
+        rows = out[c * 18000:(c + 1) * 18000]
+        assert float((rows - alone).abs().max()) <= 2e-6 * max(1.0, float(alone.abs().max()))
+    # per-resolution checksums of the whole batch equal the sum of the per-clip checksums (double precision)
+    total = out.double().sum(dim=0)
+    per_clip = sum(out[c * 18000:(c + 1) * 18000].double().sum(dim=0) for c in range(nc))
+    assert torch.allclose(total, per_clip, rtol=1e-12)
+    x_last = sig[(nc - 1) * n:].cpu().numpy()
+    start = 441 * (18000 - 130)                    # a multiple of the hop: frame j of the excerpt is frame 17870 + j
+    want_tail = ref.rnn_beat_preprocessor()(x_last[start:])            # the last 130 frames run past the end of the stem
+    assert want_tail.shape[0] == 130
+    assert_close(out[-100:].cpu().numpy(), want_tail[-100:], what="tail of the last stem")
+    x0 = sig[:n].cpu().numpy()
+    assert_close(out[:90].cpu().numpy(), ref.rnn_beat_preprocessor()(x0[:SR + 4096])[:90], what="head of the first stem")
