@@ -28,10 +28,34 @@ namespace b2 {
 template <int MS_>
 struct MagLinear {
   static constexpr int MS = MS_;
+  static B2_HD int batch_offset(int h) { return h * MS_; }
   template <int TBF>
   static B2_HD void load(const float *mags, int k, float (&m)[TBF]) {
 #pragma unroll
     for (int t = 0; t < TBF; ++t) m[t] = mags[t * MS + k];
+  }
+};
+// MagInterleaved: the TB frames of a tail batch are interleaved per bin (bin k of frame t at k * TB + t), so
+// pass 3 of the pair kernel stores both frames of a pair with one 64-bit store and the filterbank fetches
+// all frames of a bin with one vector load (k_front_pair; TB = TBF = 2 or 4).
+template <int TB, int MS_>
+struct MagInterleaved {
+  static constexpr int MS = MS_;
+  static B2_HD int batch_offset(int h) { return h; }
+  template <int TBF>
+  static B2_HD void load(const float *mags, int k, float (&m)[TBF]) {
+    static_assert(TBF == TB && (TB == 2 || TB == 4), "one vector per bin");
+    if (TB == 2) {
+      const float2 v = *reinterpret_cast<const float2 *>(mags + k * 2);
+      m[0] = v.x;
+      m[1] = v.y;
+    } else {
+      const float4 v = *reinterpret_cast<const float4 *>(mags + k * 4);
+      m[0] = v.x;
+      m[1] = v.y;
+      m[TBF > 2 ? 2 : 0] = v.z;
+      m[TBF > 2 ? 3 : 0] = v.w;
+    }
   }
 };
 // MagInPlace: k_front_pair for frame 4096 has no room for a separate magnitude buffer; pass 3 overwrites
@@ -41,6 +65,7 @@ struct MagLinear {
 template <int F2, int MS_>
 struct MagInPlace {
   static constexpr int MS = MS_;
+  static B2_HD int batch_offset(int) { return 0; }
   static B2_HD int at(int k) { return 2 * fft_col_offset<F2>(k & 255) + 2 * (k >> 8); }
   template <int TBF>
   static B2_HD void load(const float *mags, int k, float (&m)[TBF]) {

@@ -245,7 +245,7 @@ __device__ __forceinline__ int front_tail(const FrontParams &p, const TailCtx &c
     const int fh = fb + h;
     if (fh >= f1) break;
     if (h > 0) group_bar(g);                     // the previous sub-batch is done with s_partial
-    const float *hmags = s_mags + h * MS;
+    const float *hmags = s_mags + MA::batch_offset(h);
     // ---- K2a: slab filterbank ----
     if (p.fb_w4_global) {
       if (p.power) fb_slabs<15, TBF, MA, true, true>(p.fb_w4, hmags, s_partial, p.fb_ns, p.fb_kmin, pstride, tid, cap);

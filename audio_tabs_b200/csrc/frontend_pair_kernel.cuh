@@ -38,7 +38,14 @@ struct PairCfg {
 #else
   static constexpr bool INPLACE = false;
 #endif
+#ifdef B2_PAIR_MAG_LINEAR   // tuning: one row of MS floats per frame instead of frames interleaved per bin
   using MA = typename std::conditional<INPLACE, MagInPlace<2 * F, MS>, MagLinear<MS>>::type;
+  static constexpr bool INTERLEAVED = false;
+#else
+  static constexpr bool INTERLEAVED = !INPLACE && (TB == TBF) && (TB == 2 || TB == 4);
+  using MA = typename std::conditional<INPLACE, MagInPlace<2 * F, MS>,
+                                       typename std::conditional<INTERLEAVED, MagInterleaved<TB, MS>, MagLinear<MS>>::type>::type;
+#endif
   // TMA staging: once pass 3 has consumed the FFT buffer, one thread starts a bulk copy (cp.async.bulk,
   // completion on an mbarrier) of the raw samples the FIRST step of the next tail batch needs into that
   // buffer; it lands while the filterbank / band stage runs, and pass 1 then reads shared memory instead
@@ -261,6 +268,8 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front_pair(const FrontP
           auto put = [&](int bin, float ma, float mb) {
             if (P::INPLACE) {
               *reinterpret_cast<float2 *>(s_mags + MagInPlace<F2, MS>::at(bin)) = make_float2(ma, mb);
+            } else if (P::INTERLEAVED) {   // frames sub + 2 sl and the next one sit side by side
+              *reinterpret_cast<float2 *>(s_mags + bin * TB + sub + 2 * sl) = make_float2(ma, mb);
             } else {
               magsA[bin] = ma;
               magsB[bin] = mb;
