@@ -272,12 +272,19 @@ __device__ __forceinline__ int front_tail(const FrontParams &p, const TailCtx &c
       float ysum[TBF];
 #pragma unroll
       for (int t = 0; t < TBF; ++t) ysum[t] = 0.f;
-      const float *pp = s_partial + bd.x;
+      if (PartialLayout<TBF>::ADJACENT) {        // slab band: partial sums of the slabs it touches
+        const float *pp = s_partial + bd.x * TBF;
 #pragma unroll 4
-      for (int i = 0; i < nP; ++i) {             // slab band: partial sums of the slabs it touches
-        const bool on = i < bd.y;
+        for (int i = 0; i < nP; ++i)
+          if (i < bd.y) FrameVec<TBF>::add(pp + 4 * TBF * i, ysum);
+      } else {
+        const float *pp = s_partial + bd.x;
+#pragma unroll 4
+        for (int i = 0; i < nP; ++i) {
+          const bool on = i < bd.y;
 #pragma unroll
-        for (int t = 0; t < TBF; ++t) ysum[t] += on ? pp[t * pstride + 4 * i] : 0.f;
+          for (int t = 0; t < TBF; ++t) ysum[t] += on ? pp[t * pstride + 4 * i] : 0.f;
+        }
       }
       const float *dwp = s_dw + bd.x;
 #pragma unroll 2
