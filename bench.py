@@ -109,14 +109,14 @@ class ClockSampler:
             self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS,
-                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.file, stderr=subprocess.DEVNULL)
+                 "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.file, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, settle=0.15):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(settle)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -247,12 +247,12 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize(dev)
 
     # ---- device-resident timing: W warm-up, exactly K timed steps ---------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()           # nvidia-smi needs ~0.1 s to come up: start it before the warm-up
     for _ in range(args.warmup):
         fe.run_packed(packed, out)
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = _ffi.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launch_events = []      # (resolution, start, end) of every front-end launch inside the timed region
@@ -264,7 +264,15 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     launches = _ffi.launch_count() - launches0
     elapsed_ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
+    # the timed region is ~0.1 s: keep the SAME load running (untimed) until the sampler has a handful of
+    # readings, so that none of them is taken on an idle GPU
+    t_keep = time.perf_counter()
+    while time.perf_counter() - t_keep < 0.6:
+        fe.run_packed(packed, out)
+        torch.cuda.synchronize(dev)
+    clocks = sampler.stop(settle=0.0) if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = "warm-up + timed steps + 0.6 s of the same steps (GPU never idle while sampled)"
     if world > 1:
         t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
