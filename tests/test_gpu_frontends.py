@@ -451,3 +451,46 @@ def test_full_config2_batch_properties(b2):
     assert_close(out[-100:].cpu().numpy(), want_tail[-100:], what="tail of the last stem")
     x0 = sig[:n].cpu().numpy()
     assert_close(out[:90].cpu().numpy(), ref.rnn_beat_preprocessor()(x0[:SR + 4096])[:90], what="head of the first stem")
+
+
+# ---- framing options: origin, end, fractional hop, hop > frame, task-boundary lengths ----------------
+@pytest.mark.parametrize("kw", [
+    dict(frame_size=2048, hop_size=441.0, origin="right"),          # 'future' frames: origin = -(frame/2)
+    dict(frame_size=2048, hop_size=441.0, origin="left"),           # 'past' frames: origin = (frame-1)/2
+    dict(frame_size=1024, hop_size=441.0, origin=100),
+    dict(frame_size=4096, hop_size=441.0, end="extend"),
+    dict(frame_size=2048, fps=123.4),                               # fractional hop 357.37...
+    dict(frame_size=1024, hop_size=2500.0),                         # hop > frame: gaps between frames
+    dict(frame_size=4096, fps=7),                                   # hop 6300: low-overlap regime
+])
+def test_framing_options(b2, kw):
+    from audio_tabs_b200.synth import synth_guitar
+    x = synth_guitar(3500 + len(str(kw)), 2.3)
+
+    def chain(m):
+        return m.SequentialProcessor((
+            m.SignalProcessor(num_channels=1, sample_rate=SR), m.FramedSignalProcessor(**kw),
+            m.ShortTimeFourierTransformProcessor(), m.FilteredSpectrogramProcessor(num_bands=12, fmin=30, fmax=17000),
+            m.LogarithmicSpectrogramProcessor(mul=1, add=1),
+            m.SpectrogramDifferenceProcessor(diff_ratio=0.5, positive_diffs=True, stack_diffs=np.hstack)))
+    want = np.asarray(chain(ref)(x))
+    got = np.asarray(chain(b2)(x))
+    assert got.shape == want.shape
+    assert_close(got, want, what=str(kw))
+
+
+def test_clip_lengths_around_task_boundaries(b2):
+    """Frame counts that straddle the 92-95-frame tasks, the tail batches of 2 / 4 frames and the frame pairs
+    (odd counts, one frame, counts just above and below a task), all in one packed batch."""
+    from audio_tabs_b200.frontends import beat_specs
+    from audio_tabs_b200.plan import FrontEnd
+    from audio_tabs_b200.synth import synth_guitar
+    base = synth_guitar(3600, 3.0)
+    counts = [1, 2, 3, 5, 91, 92, 93, 94, 95, 96, 97, 98, 187, 189, 191, 193]
+    clips = [base[:441 * (c - 1) + 17 + i] for i, c in enumerate(counts)]
+    fe = FrontEnd(beat_specs(), device=0)
+    outs = fe.process_batch(clips)
+    for c, clip, got in zip(counts, clips, outs):
+        want = ref.rnn_beat_preprocessor()(clip)
+        assert got.shape == want.shape == (c, 314)
+        assert_close(got, want, what="%d frames" % c)
