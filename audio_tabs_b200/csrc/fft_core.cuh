@@ -64,34 +64,57 @@ struct FftCfg {
 };
 
 // ---- complex helpers ---------------------------------------------------------------------------
-// On sm_100 a complex add/subtract is ONE packed-FP32 instruction (FADD2 / FFMA2 on a 64-bit
-// register pair) instead of two scalar ones; the host build (tests/emu) uses the scalar form.
+// On sm_100 every complex add / subtract / rotate-by-i is ONE packed-FP32 instruction on a 64-bit
+// register pair and a complex multiply is TWO (FMUL2 + FFMA2): the packed instructions take a
+// half-swap (LO_HI), a per-half negation (NP / PN) and a scalar broadcast (.F32) as operand
+// modifiers, and ptxas folds the component shuffles written below into them (checked with
+// cuobjdump: no MOV / PRMT is left).  The host build (tests/emu) uses the scalar form.
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000) && !defined(B2_NO_PACKED_F32)
 #define B2_PACKED_F32 1
 B2_HD float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
-B2_HD float2 csub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
-B2_HD float2 cadd_conj(float2 a, float2 b) { return __ffma2_rn(b, make_float2(1.f, -1.f), a); }   // a + conj(b)
-B2_HD float2 csub_conj(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, 1.f), a); }   // a - conj(b)
-B2_HD float2 emul(float2 a, float2 b) { return __fmul2_rn(a, b); }                                   // element-wise
+B2_HD float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+B2_HD float2 cadd_conj(float2 a, float2 b) { return __fadd2_rn(a, make_float2(b.x, -b.y)); }   // a + conj(b)
+B2_HD float2 csub_conj(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, b.y)); }   // a - conj(b)
+B2_HD float2 cadd_negi(float2 a, float2 b) { return __fadd2_rn(a, make_float2(b.y, -b.x)); }   // a - i b
+B2_HD float2 cadd_posi(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.y, b.x)); }   // a + i b
+B2_HD float2 emul(float2 a, float2 b) { return __fmul2_rn(a, b); }                               // element-wise
+B2_HD float2 crscale(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
+B2_HD float2 cmul(float2 a, float2 b) {
+  return __ffma2_rn(make_float2(a.y, a.x), make_float2(-b.y, b.y), __fmul2_rn(a, make_float2(b.x, b.x)));
+}
 #else
 B2_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 B2_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 B2_HD float2 cadd_conj(float2 a, float2 b) { return make_float2(a.x + b.x, a.y - b.y); }
 B2_HD float2 csub_conj(float2 a, float2 b) { return make_float2(a.x - b.x, a.y + b.y); }
+B2_HD float2 cadd_negi(float2 a, float2 b) { return make_float2(a.x + b.y, a.y - b.x); }
+B2_HD float2 cadd_posi(float2 a, float2 b) { return make_float2(a.x - b.y, a.y + b.x); }
 B2_HD float2 emul(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
-#endif
+B2_HD float2 crscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
 B2_HD float2 cmul(float2 a, float2 b) {
-  return make_float2(fmaf(a.x, b.x, -(a.y * b.y)), fmaf(a.x, b.y, a.y * b.x));
+  return make_float2(fmaf(-a.y, b.y, a.x * b.x), fmaf(a.x, b.y, a.y * b.x));
 }
+#endif
 B2_HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+// Store of a complex value into SHARED memory.  Written as a plain float2 assignment ptxas copies
+// every result of a packed instruction into a staging pair first (MOV, MOV, STS.64 -- checked with
+// cuobjdump on CUDA 12.9); the explicit st.shared.v2.f32 takes the pair the arithmetic left it in.
+B2_HD void cstore(float2 *p, float2 v) {
+#if defined(B2_PACKED_F32)
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"((unsigned)__cvta_generic_to_shared(p)), "f"(v.x), "f"(v.y)
+               : "memory");
+#else
+  *p = v;
+#endif
+}
 B2_HD float2 mul_neg_i(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
 
 constexpr float kH = 0.70710678118654752440f;   // sqrt(1/2)
 constexpr float kC1 = 0.92387953251128675613f;  // cos(pi/8)
 constexpr float kS1 = 0.38268343236508977173f;  // sin(pi/8)
 
-B2_HD float2 mul_w8_1(float2 a) { return make_float2(kH * (a.x + a.y), kH * (a.y - a.x)); }    // * (h,-h)
-B2_HD float2 mul_w8_3(float2 a) { return make_float2(kH * (a.y - a.x), -kH * (a.x + a.y)); }   // * (-h,-h)
+B2_HD float2 mul_w8_1(float2 a) { return crscale(cadd_negi(a, a), kH); }    // * (h,-h):  h (a - i a)
+B2_HD float2 mul_w8_3(float2 a) { return crscale(cadd_posi(a, a), -kH); }   // * (-h,-h): -h (a + i a)
 
 // ---- in-register DFTs (forward, W = exp(-2 pi i / R)) ------------------------------------------
 B2_HD void dft2(float2 &a, float2 &b) {
@@ -103,11 +126,11 @@ B2_HD void dft2(float2 &a, float2 &b) {
 // natural order in, natural order out
 B2_HD void dft4(float2 &x0, float2 &x1, float2 &x2, float2 &x3) {
   float2 t0 = cadd(x0, x2), t1 = csub(x0, x2);
-  float2 t2 = cadd(x1, x3), d = csub(x1, x3);   // t3 = -i d = (d.y, -d.x), applied component-wise
+  float2 t2 = cadd(x1, x3), d = csub(x1, x3);   // t3 = -i d, folded into the two adds below
   x0 = cadd(t0, t2);
   x2 = csub(t0, t2);
-  x1 = make_float2(t1.x + d.y, t1.y - d.x);
-  x3 = make_float2(t1.x - d.y, t1.y + d.x);
+  x1 = cadd_negi(t1, d);
+  x3 = cadd_posi(t1, d);
 }
 
 // in place; X[k] ends up at v[pos8(k)]
@@ -177,7 +200,7 @@ B2_HD void fft_pass1(Load load, float2 *p) {
   for (int n1 = 0; n1 < 16; ++n1) v[n1] = load(n1);
   dft16(v);
 #pragma unroll
-  for (int k1 = 0; k1 < 16; ++k1) p[k1 * C::S1] = v[dft_pos<16>(k1)];
+  for (int k1 = 0; k1 < 16; ++k1) cstore(p + k1 * C::S1, v[dft_pos<16>(k1)]);
 }
 
 // ---- pass 2: twiddle W_256^(n2*k1), DFT16 over n2, in place ------------------------------------
@@ -192,7 +215,7 @@ B2_HD void fft_pass2(const float2 (&tw2)[16], float2 *p) {
   for (int n2 = 1; n2 < 16; ++n2) v[n2] = cmul(v[n2], tw2[n2]);
   dft16(v);
 #pragma unroll
-  for (int k2 = 0; k2 < 16; ++k2) p[k2 * C::R3] = v[dft_pos<16>(k2)];
+  for (int k2 = 0; k2 < 16; ++k2) cstore(p + k2 * C::R3, v[dft_pos<16>(k2)]);
 }
 
 // column q = k1 + 16*k2 of the pass-2 output starts at this offset (elements n3 = 0..R3-1 follow)
@@ -200,6 +223,39 @@ template <int F>
 B2_HD constexpr int fft_col_offset(int q) {
   return (q & 15) * FftCfg<F>::S1 + (q >> 4) * FftCfg<F>::R3;
 }
+
+// Twiddles of the last pass: W^(n3 q), n3 = 1..R3-1, from the table rows n3 = 1, 2, 4, 8 and R3-5 complex
+// products -- shared-memory wavefronts, not FP32 issue slots, are the scarcer resource in these kernels
+// (profiles/README.md); the extra rounding (<= 3 products deep) is ~2e-7 relative.  -DB2_TW3_TABLE reads
+// all R3-1 rows instead.
+template <int R3>
+B2_HD void tw3_rows(const float2 *tw3q, float2 (&w)[R3]) {
+#if defined(B2_TW3_TABLE)
+#pragma unroll
+  for (int n3 = 1; n3 < R3; ++n3) w[n3] = tw3q[n3 * 129];
+#else
+#pragma unroll
+  for (int n3 = 1; n3 < R3; n3 *= 2) w[n3] = tw3q[n3 * 129];
+#pragma unroll
+  for (int n3 = 3; n3 < R3; ++n3)
+    if (n3 & (n3 - 1)) {
+      const int hi = n3 >= 8 ? 8 : n3 >= 4 ? 4 : 2;
+      w[n3] = cmul(w[hi], w[n3 - hi]);
+    }
+#endif
+}
+
+// cos / sin of j pi / 16, j in [0,16): W_(2 R3)^k3 = (cos_pi16(j), -sin_pi16(j)) with j = k3 * 16 / R3
+// (functions, not namespace-scope tables: the index is a constant only after unrolling)
+B2_HD constexpr float cos_pi16(int j) {
+  constexpr float t[16] = {1.f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+                           0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f,
+                           0.19509032201612826785f, 0.f, -0.19509032201612826785f, -0.38268343236508977173f,
+                           -0.55557023301960222474f, -0.70710678118654752440f, -0.83146961230254523708f,
+                           -0.92387953251128675613f, -0.98078528040323044913f};
+  return t[j];
+}
+B2_HD constexpr float sin_pi16(int j) { return j < 8 ? cos_pi16(8 - j) : cos_pi16(j - 8); }
 
 // ---- pass 3: last radix-R3 pass fused with the real-spectrum split -----------------------------
 // unit u in [1,127]: pa / pb = columns u and 256-u; tw3u = tw3 + u (tw3[n3*129 + q] = W_N^(n3 q));
@@ -217,18 +273,28 @@ B2_HD void fft_pass3_unit(int u, const float2 *pa, const float2 *pb, const float
     P[n3] = cadd_conj(a, b);  // a + conj(b)
     M[n3] = csub_conj(a, b);  // a - conj(b)
   }
+  {
+    float2 w[R3];
+    tw3_rows<R3>(tw3u, w);
 #pragma unroll
-  for (int n3 = 1; n3 < R3; ++n3) {
-    float2 w = tw3u[n3 * 129];
-    P[n3] = cmul(P[n3], w);
-    M[n3] = cmul(M[n3], w);
+    for (int n3 = 1; n3 < R3; ++n3) {
+      P[n3] = cmul(P[n3], w[n3]);
+      M[n3] = cmul(M[n3], w[n3]);
+    }
   }
   Dft<R3>::run(P);
   Dft<R3>::run(M);
+  const float2 pt0 = ptu[0];   // pt[k3*129 + u] = pt[u] * W_(2 R3)^k3: one load, the rest are constants
 #pragma unroll
   for (int k3 = 0; k3 < R3; ++k3) {
     float2 E = P[dft_pos<R3>(k3)];
+#if defined(B2_TW3_TABLE)
     float2 T = cmul(M[dft_pos<R3>(k3)], ptu[k3 * 129]);
+#else
+    float2 T = M[dft_pos<R3>(k3)];
+    if (k3 > 0) T = cmul(T, make_float2(cos_pi16(k3 * (16 / R3)), -sin_pi16(k3 * (16 / R3))));
+    T = cmul(T, pt0);
+#endif
     const int k = u + 256 * k3;
     emit(k, cadd(E, T));
     emit(C::N - k, cconj(csub(E, T)));
@@ -319,11 +385,14 @@ B2_HD void fft_pair_pass3_unit(int u, const float2 *pa, const float2 *pb, const 
     P[n3] = cadd_conj(a, b);
     M[n3] = csub_conj(a, b);
   }
+  {
+    float2 w[R3];
+    tw3_rows<R3>(tw3u, w);
 #pragma unroll
-  for (int n3 = 1; n3 < R3; ++n3) {
-    float2 w = tw3u[n3 * 129];
-    P[n3] = cmul(P[n3], w);
-    M[n3] = cmul(M[n3], w);
+    for (int n3 = 1; n3 < R3; ++n3) {
+      P[n3] = cmul(P[n3], w[n3]);
+      M[n3] = cmul(M[n3], w[n3]);
+    }
   }
   Dft<R3>::run(P);
   Dft<R3>::run(M);

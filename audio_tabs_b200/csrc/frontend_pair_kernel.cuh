@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front_pair(const FrontP
               const float *wp = w1 + it * kGroupThreads;
               fft_pass1<F2>([&](int n1) {
                 const float w = wp[n1 * C2::BPF];
-                return make_float2(w * xa[it * 16 + n1], w * xb[it * 16 + n1]);
+                return crscale(make_float2(xa[it * 16 + n1], xb[it * 16 + n1]), w);
               }, p1 + it * kGroupThreads);
             }
           } else
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front_pair(const FrontP
               const void *qa = S.ptr(sA + b), *qb = S.ptr(sB + b);
               fft_pass1<F2>([&](int n1) {
                 const float w = wp[n1 * C2::BPF];
-                return make_float2(w * Samples<IN>::at_ptr(qa, n1 * C2::BPF), w * Samples<IN>::at_ptr(qb, n1 * C2::BPF));
+                return crscale(make_float2(Samples<IN>::at_ptr(qa, n1 * C2::BPF), Samples<IN>::at_ptr(qb, n1 * C2::BPF)), w);
               }, p1 + it * kGroupThreads);
             } else {
               fft_pass1<F2>([&](int n1) {
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front_pair(const FrontP
                 const long long a = sA + n1 * C2::BPF + b, bb = sB + n1 * C2::BPF + b;
                 const float xa = (a >= 0 && a < nsamp) ? S.at(a) : 0.f;
                 const float xb = (hasB && bb >= 0 && bb < nsamp) ? S.at(bb) : 0.f;
-                return make_float2(w * xa, w * xb);
+                return crscale(make_float2(xa, xb), w);
               }, p1 + it * kGroupThreads);
             }
           }
