@@ -70,6 +70,10 @@ struct ResPlan {
   float *d_window = nullptr;
   float2 *d_tw2 = nullptr, *d_tw3 = nullptr, *d_pt = nullptr, *d_wr = nullptr;
   float2 *d_pair_tw3 = nullptr, *d_pair_wr = nullptr;   // F-point tables of the pair transform (F <= 4096)
+  int win_fly = 0;                                      // the window is a scaled np.hanning(F): evaluated in registers
+  float win_h = 0.f;
+  float2 win_cs[16] = {};
+  float2 *d_win_ab = nullptr;
   int fb_L = 3, fb_ns = 1, fb_kmin = 0, fb_ndw = 0, fb_ndirect = 0, fb_w4_global = 0;
   float4 *d_fb_w4 = nullptr;
   int4 *d_fb_band = nullptr;
@@ -180,6 +184,35 @@ int build_res(b200spec_plan *pl, const b200spec_res_desc &d, ResPlan &r) {
     }
     if ((rc = upload(pl, ptw3.data(), ptw3.size(), &r.d_pair_tw3))) return rc;
     if ((rc = upload(pl, pwr.data(), pwr.size(), &r.d_pair_wr))) return rc;
+    // Is the window s * np.hanning(F) (madmom's default, / 32767 for int16)?  Then the pair kernel forms
+    // 0.5 w[n] = H - H cos(2 pi n / (F-1)), H = s / 4, by angle addition instead of loading it.
+    double sw = 0.0, shh = 0.0;
+    std::vector<double> hann(F);
+    for (int i = 0; i < F; ++i) {
+      hann[i] = 0.5 - 0.5 * cos(2.0 * PI * (double)i / (double)(F - 1));
+      sw += (double)d.window[i] * hann[i];
+      shh += hann[i] * hann[i];
+    }
+    const double sc = sw / shh;
+    double dev = 0.0;
+    for (int i = 0; i < F; ++i) dev = std::max(dev, fabs((double)d.window[i] - sc * hann[i]));
+    const char *wf = getenv("B200SPEC_WINFLY");
+    if (sc > 0.0 && dev <= 1.5e-7 * sc && !(wf && wf[0] == '0')) {
+      const int bpf = F / 16;
+      const double H = 0.25 * sc;
+      r.win_fly = 1;
+      r.win_h = (float)H;
+      for (int n1 = 0; n1 < 16; ++n1) {
+        const double a = 2.0 * PI * (double)(n1 * bpf) / (double)(F - 1);
+        r.win_cs[n1] = make_float2((float)cos(a), (float)sin(a));
+      }
+      std::vector<float2> ab(bpf);
+      for (int b = 0; b < bpf; ++b) {
+        const double t = 2.0 * PI * (double)b / (double)(F - 1);
+        ab[b] = make_float2((float)(-H * cos(t)), (float)(H * sin(t)));
+      }
+      if ((rc = upload(pl, ab.data(), ab.size(), &r.d_win_ab))) return rc;
+    }
   }
 
   // banded filterbank -> interleaved slices of at most `seg_max` taps
@@ -314,6 +347,10 @@ int launch_front(const b200spec_plan *pl, int res, int mode, const void *d_sig, 
   p.hop = r.hop;
   p.origin = r.origin;
   p.window = r.d_window;
+  p.win_fly = r.win_fly;
+  p.win_h = r.win_h;
+  for (int i = 0; i < 16; ++i) p.win_cs[i] = r.win_cs[i];
+  p.win_ab = r.d_win_ab;
   p.tw2 = r.d_tw2;
   p.tw3 = r.d_tw3;
   p.pt = r.d_pt;

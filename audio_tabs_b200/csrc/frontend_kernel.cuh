@@ -40,6 +40,15 @@ struct FrontParams {
   int origin;
   // tables (plan-owned, device)
   const float *window;  // F, already * 1/2 (and / 32767 for int16)
+  // Hann window evaluated in registers by the pair kernel (win_fly != 0; the table above stays for the
+  // clip edges and for any other window):  w[b + n1 BPF] = win_h + A_b C[n1] + B_b S[n1]  with
+  // (A_b, B_b) = win_ab[b] = (-H cos t_b, H sin t_b), t_b = 2 pi b / (F-1), (C, S)[n1] = win_cs[n1] =
+  // (cos, sin)(2 pi n1 BPF / (F-1)) -- kernel-parameter constants, so the products take them from the
+  // constant bank and the per-sample window value costs no load at all
+  int win_fly;
+  float win_h;
+  float2 win_cs[16];
+  const float2 *win_ab; // [BPF of the pair geometry = F / 16]
   const float2 *tw2;    // [16][16]   tw2[k1*16 + n2] = W_256^(n2 k1)
   const float2 *tw3;    // [R3][129]  tw3[n3*129 + q] = W_N^(n3 q)
   const float2 *pt;     // [R3][129]  pt[k3*129 + q]  = -i W_F^(q + 256 k3)

@@ -141,6 +141,11 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front_pair(const FrontP
   const int b12 = (PPS > 1) ? tid % C2::BPF : tid;          // butterfly index in pass 1/2 (first iteration)
   float2 *p1 = buf + sl12 * C2::BUF + b12;                              // pass-1 store base
   const float *w1 = s_win + b12;                                        // window value of this butterfly's n1 = 0
+  float2 wab0 = make_float2(0.f, 0.f), wab1 = wab0;                     // Hann window in registers (FrontParams::win_fly)
+  if (p.win_fly) {
+    wab0 = __ldg(p.win_ab + b12);
+    if (C2::IT12 > 1) wab1 = __ldg(p.win_ab + b12 + kGroupThreads);
+  }
   float2 *p2 = buf + sl12 * C2::BUF + (b12 & 15) * S1 + (b12 >> 4);     // pass-2 in-place base (k1, n3)
   const int u = tid;                                                    // pass-3 unit (0..127, all active)
   const int pa_off = fft_col_offset<F2>(u), pb_off = fft_col_offset<F2>((256 - u) & 255);
@@ -225,7 +230,14 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front_pair(const FrontP
           for (int it = 0; it < C2::IT12; ++it) {
             const int b = b12 + it * kGroupThreads;
             const float *wp = w1 + it * kGroupThreads;
-            if (interior) {
+            if (interior && p.win_fly) {
+              const void *qa = S.ptr(sA + b), *qb = S.ptr(sB + b);
+              const float2 ab = it ? wab1 : wab0;
+              fft_pass1<F2>([&](int n1) {
+                const float w = fmaf(ab.x, p.win_cs[n1].x, fmaf(ab.y, p.win_cs[n1].y, p.win_h));
+                return crscale(make_float2(Samples<IN>::at_ptr(qa, n1 * C2::BPF), Samples<IN>::at_ptr(qb, n1 * C2::BPF)), w);
+              }, p1 + it * kGroupThreads);
+            } else if (interior) {
               const void *qa = S.ptr(sA + b), *qb = S.ptr(sB + b);
               fft_pass1<F2>([&](int n1) {
                 const float w = wp[n1 * C2::BPF];

@@ -494,3 +494,20 @@ def test_clip_lengths_around_task_boundaries(b2):
         want = ref.rnn_beat_preprocessor()(clip)
         assert got.shape == want.shape == (c, 314)
         assert_close(got, want, what="%d frames" % c)
+
+
+@pytest.mark.parametrize("window", [np.hamming, np.blackman, None], ids=["hamming", "blackman", "rectangular"])
+def test_other_windows_use_the_table_path(b2, window):
+    """np.hanning is evaluated in registers by the pair kernel; any other window must come from the table."""
+    x = noise(21, 50000) * 0.3
+    for frame_size in (1024, 4096):
+        rs = ref.spectrogram(ref.ShortTimeFourierTransform(
+            ref.FramedSignal(ref.Signal(x, sample_rate=SR), frame_size=frame_size), window=window))
+        want = ref.logarithmic_spectrogram(ref.filtered_spectrogram(rs, num_bands=12), mul=1, add=1).data
+        want = np.hstack([want, ref.spectrogram_difference(want, 1, positive_diffs=True)])
+        stft = b2.ShortTimeFourierTransform(b2.FramedSignal(b2.Signal(x, sample_rate=SR), frame_size=frame_size),
+                                            window=window)
+        log = b2.LogarithmicSpectrogram(b2.FilteredSpectrogram(b2.Spectrogram(stft), num_bands=12), mul=1, add=1)
+        got = np.asarray(b2.SpectrogramDifferenceProcessor(diff_frames=1, positive_diffs=True, stack_diffs=np.hstack)(log))
+        assert got.shape == want.shape
+        assert_close(got, want, what="log spec + diff, frame %d" % frame_size)
