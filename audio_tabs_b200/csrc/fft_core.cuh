@@ -203,6 +203,23 @@ B2_HD void fft_pass1(Load load, float2 *p) {
   for (int k1 = 0; k1 < 16; ++k1) cstore(p + k1 * C::S1, v[dft_pos<16>(k1)]);
 }
 
+// two pass-1 butterflies of one thread with all 32 (pairs of) loads issued before the arithmetic
+template <int F, class LoadA, class LoadB>
+B2_HD void fft_pass1_x2(LoadA load_a, LoadB load_b, float2 *p, int d) {
+  using C = FftCfg<F>;
+  float2 v[16], w[16];
+#pragma unroll
+  for (int n1 = 0; n1 < 16; ++n1) v[n1] = load_a(n1);
+#pragma unroll
+  for (int n1 = 0; n1 < 16; ++n1) w[n1] = load_b(n1);
+  dft16(v);
+  dft16(w);
+#pragma unroll
+  for (int k1 = 0; k1 < 16; ++k1) cstore(p + k1 * C::S1, v[dft_pos<16>(k1)]);
+#pragma unroll
+  for (int k1 = 0; k1 < 16; ++k1) cstore(p + d + k1 * C::S1, w[dft_pos<16>(k1)]);
+}
+
 // ---- pass 2: twiddle W_256^(n2*k1), DFT16 over n2, in place ------------------------------------
 // thread (k1, n3): p = buf + k1 * S1 + n3; element n2 sits at p[n2 * R3]; output k2 replaces it.
 template <int F>
@@ -216,6 +233,28 @@ B2_HD void fft_pass2(const float2 (&tw2)[16], float2 *p) {
   dft16(v);
 #pragma unroll
   for (int k2 = 0; k2 < 16; ++k2) cstore(p + k2 * C::R3, v[dft_pos<16>(k2)]);
+}
+
+// two independent pass-2 butterflies of one thread (p and p + d) with their loads issued together: twice the
+// instruction-level parallelism where a thread has two to do (frame 4096 of the pair kernel)
+template <int F>
+B2_HD void fft_pass2_x2(const float2 (&tw2)[16], float2 *p, int d) {
+  using C = FftCfg<F>;
+  float2 v[16], w[16];
+#pragma unroll
+  for (int n2 = 0; n2 < 16; ++n2) v[n2] = p[n2 * C::R3];
+#pragma unroll
+  for (int n2 = 0; n2 < 16; ++n2) w[n2] = p[d + n2 * C::R3];
+#pragma unroll
+  for (int n2 = 1; n2 < 16; ++n2) v[n2] = cmul(v[n2], tw2[n2]);
+#pragma unroll
+  for (int n2 = 1; n2 < 16; ++n2) w[n2] = cmul(w[n2], tw2[n2]);
+  dft16(v);
+  dft16(w);
+#pragma unroll
+  for (int k2 = 0; k2 < 16; ++k2) cstore(p + k2 * C::R3, v[dft_pos<16>(k2)]);
+#pragma unroll
+  for (int k2 = 0; k2 < 16; ++k2) cstore(p + d + k2 * C::R3, w[dft_pos<16>(k2)]);
 }
 
 // column q = k1 + 16*k2 of the pass-2 output starts at this offset (elements n3 = 0..R3-1 follow)

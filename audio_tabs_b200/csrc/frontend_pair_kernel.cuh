@@ -226,6 +226,22 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front_pair(const FrontP
               }, p1 + it * kGroupThreads);
             }
           } else
+#if defined(B2_P1_X2)
+          if (C2::IT12 == 2 && interior && p.win_fly) {     // both butterflies of this thread, loads issued together
+            const void *qa = S.ptr(sA + b12), *qb = S.ptr(sB + b12);
+            fft_pass1_x2<F2>(
+                [&](int n1) {
+                  const float w = fmaf(wab0.x, p.win_cs[n1].x, fmaf(wab0.y, p.win_cs[n1].y, p.win_h));
+                  return crscale(make_float2(Samples<IN>::at_ptr(qa, n1 * C2::BPF), Samples<IN>::at_ptr(qb, n1 * C2::BPF)), w);
+                },
+                [&](int n1) {
+                  const float w = fmaf(wab1.x, p.win_cs[n1].x, fmaf(wab1.y, p.win_cs[n1].y, p.win_h));
+                  return crscale(make_float2(Samples<IN>::at_ptr(qa, n1 * C2::BPF + kGroupThreads),
+                                             Samples<IN>::at_ptr(qb, n1 * C2::BPF + kGroupThreads)), w);
+                },
+                p1, kGroupThreads);
+          } else
+#endif
 #pragma unroll 1
           for (int it = 0; it < C2::IT12; ++it) {
             const int b = b12 + it * kGroupThreads;
@@ -267,6 +283,12 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front_pair(const FrontP
         group_bar(g);
         // ---------------- pass 2: twiddle, DFT16, in place ----------------
         if (fA < f1) {
+          // frame 4096: both butterflies of the thread with their loads issued together (the kernels are latency
+          // bound, not throughput bound: -1.9 % on B200; -DB2_NO_P2_X2 restores the loop)
+#if !defined(B2_NO_P2_X2)
+          if (C2::IT12 == 2) fft_pass2_x2<F2>(tw2r, p2, kGroupThreads >> 4);
+          else
+#endif
 #pragma unroll 1
           for (int it = 0; it < C2::IT12; ++it) fft_pass2<F2>(tw2r, p2 + it * (kGroupThreads >> 4));
         }
