@@ -529,6 +529,10 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
         group_bar(g);
         // ---------------- pass 2: twiddle, DFT16, in place ----------------
         if (f + fl12 < f1) {
+#if !defined(B2_NO_P2_X2)
+          if (C::IT12 == 2) fft_pass2_x2<F>(tw2r, p2, kGroupThreads >> 4);   // frame 8192: two butterflies interleaved
+          else
+#endif
 #pragma unroll 1
           for (int it = 0; it < C::IT12; ++it) fft_pass2<F>(tw2r, p2 + it * (kGroupThreads >> 4));
         }
