@@ -58,6 +58,25 @@ struct MagInterleaved {
     }
   }
 };
+// MagPairPlanes: four-frame tail batches of the pair kernel -- one plane per PAIR of frames, the two frames of
+// a pair interleaved per bin (bin k of frame t at (t / 2) * 2 MS + 2 k + (t & 1)).  Pass 3 stores a pair with
+// one 64-bit store at an 8-byte lane stride (conflict free; frames interleaved four-wide make that store
+// two-way conflicted), the filterbank fetches a bin's four frames with two 64-bit loads.
+template <int MS_>
+struct MagPairPlanes {
+  static constexpr int MS = MS_;
+  static B2_HD int batch_offset(int h) { return h; }
+  template <int TBF>
+  static B2_HD void load(const float *mags, int k, float (&m)[TBF]) {
+    static_assert(TBF == 4, "two planes of two frames");
+    const float2 a = *reinterpret_cast<const float2 *>(mags + 2 * k);
+    const float2 b = *reinterpret_cast<const float2 *>(mags + 2 * MS_ + 2 * k);
+    m[0] = a.x;
+    m[1] = a.y;
+    m[TBF > 2 ? 2 : 0] = b.x;
+    m[TBF > 2 ? 3 : 0] = b.y;
+  }
+};
 // MagInPlace: k_front_pair for frame 4096 has no room for a separate magnitude buffer; pass 3 overwrites
 // the FFT columns it has just consumed: bin k = q + 256 j of frames (A, B) sits at floats
 // 2 * column_offset(q) + 2 j + {0, 1} of the pair's buffer (F2 = 2 * frame size).  Both frames come with

@@ -41,10 +41,18 @@ struct PairCfg {
 #ifdef B2_PAIR_MAG_LINEAR   // tuning: one row of MS floats per frame instead of frames interleaved per bin
   using MA = typename std::conditional<INPLACE, MagInPlace<2 * F, MS>, MagLinear<MS>>::type;
   static constexpr bool INTERLEAVED = false;
+  static constexpr bool PLANES = false;
 #else
   static constexpr bool INTERLEAVED = !INPLACE && (TB == TBF) && (TB == 2 || TB == 4);
+#ifdef B2_PAIR_MAG_PLANES   // four-frame batches: one plane per pair of frames (conflict-free pass-3 stores;
+                            // measured slower on B200: 2.14 / 3.56 against 2.09 / 3.55 ms at frames 1024 / 2048)
+  static constexpr bool PLANES = INTERLEAVED && TB == 4;
+#else
+  static constexpr bool PLANES = false;
+#endif
   using MA = typename std::conditional<INPLACE, MagInPlace<2 * F, MS>,
-                                       typename std::conditional<INTERLEAVED, MagInterleaved<TB, MS>, MagLinear<MS>>::type>::type;
+             typename std::conditional<PLANES, MagPairPlanes<MS>,
+             typename std::conditional<INTERLEAVED, MagInterleaved<TB, MS>, MagLinear<MS>>::type>::type>::type;
 #endif
   // TMA staging: once pass 3 has consumed the FFT buffer, one thread starts a bulk copy (cp.async.bulk,
   // completion on an mbarrier) of the raw samples the FIRST step of the next tail batch needs into that
@@ -302,6 +310,8 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front_pair(const FrontP
           auto put = [&](int bin, float ma, float mb) {
             if (P::INPLACE) {
               *reinterpret_cast<float2 *>(s_mags + MagInPlace<F2, MS>::at(bin)) = make_float2(ma, mb);
+            } else if (P::PLANES) {        // plane of this pair, frames A and B side by side
+              *reinterpret_cast<float2 *>(s_mags + (sub / 2 + sl) * 2 * MS + 2 * bin) = make_float2(ma, mb);
             } else if (P::INTERLEAVED) {   // frames sub + 2 sl and the next one sit side by side
               *reinterpret_cast<float2 *>(s_mags + bin * TB + sub + 2 * sl) = make_float2(ma, mb);
             } else {
