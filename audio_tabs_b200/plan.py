@@ -411,15 +411,25 @@ class FrontEnd:
         return out
 
     # ---- pinned host in / pinned host out, copies overlapped with compute ----------------------
-    def _pipeline(self, lengths, group_clips):
-        key = (tuple(int(n) for n in lengths), int(group_clips))
+    def _pipeline(self, lengths, group_clips, n_slots=2):
+        """``group_clips``: clips per group, or a schedule of group sizes whose last entry repeats
+        (``[1, 2]`` = a short first group, then pairs)."""
+        sched = [int(group_clips)] if isinstance(group_clips, (int, np.integer)) else [int(v) for v in group_clips]
+        if not sched or min(sched) < 1:
+            raise ValueError("group sizes must be >= 1")
+        key = (tuple(int(n) for n in lengths), tuple(sched), int(n_slots))
         cache = getattr(self, "_pipe_cache", None)
         if cache is not None and cache["key"] == key:
             return cache
         groups = []
         samp0 = row0 = 0
-        for g0 in range(0, len(lengths), group_clips):
-            lens = [int(n) for n in lengths[g0:g0 + group_clips]]
+        bounds, g0 = [], 0
+        while g0 < len(lengths):
+            size = sched[min(len(bounds), len(sched) - 1)]
+            bounds.append((g0, min(len(lengths), g0 + size)))
+            g0 += size
+        for g0, g1 in bounds:
+            lens = [int(n) for n in lengths[g0:g1]]
             frames = [_ffi.num_frames(n, self.hop_size, self.end) for n in lens]
             groups.append(dict(lens=lens, frames=frames, samp0=samp0, nsamp=sum(lens), row0=row0, rows=sum(frames)))
             samp0 += sum(lens)
@@ -428,10 +438,11 @@ class FrontEnd:
         max_r = max(g["rows"] for g in groups)
         sshape = (max_s,) if self.channels == 1 else (max_s, self.channels)
         slots = [dict(sig=torch.empty(sshape, dtype=self.torch_dtype(), device=self.device),
-                      out=torch.empty((max_r, self.width), dtype=torch.float32, device=self.device)) for _ in range(2)]
+                      out=torch.empty((max_r, self.width), dtype=torch.float32, device=self.device))
+                 for _ in range(n_slots)]
         for g in groups:  # per-group offsets live on the device for the whole pipeline lifetime
             g["packed"] = [Packed(slots[s]["sig"][:g["nsamp"]], g["lens"], self.hop_size, self.end, g["frames"])
-                           for s in range(2)]
+                           for s in range(n_slots)]
         cache = dict(key=key, groups=groups, slots=slots, total_rows=row0, total_samples=samp0,
                      h2d=torch.cuda.Stream(self.device), comp=torch.cuda.Stream(self.device),
                      d2h=torch.cuda.Stream(self.device))
@@ -439,16 +450,19 @@ class FrontEnd:
         return cache
 
     def process_batch_pinned(self, host_in: torch.Tensor, lengths: Sequence[int], host_out: torch.Tensor,
-                             group_clips: int = 2) -> torch.Tensor:
+                             group_clips=(1, 2), n_slots: int = 2) -> torch.Tensor:
         """Whole batch from a pinned packed host tensor to a pinned host result matrix.
 
         Clips are processed in groups; the host->device copy of group g+1 and the device->host copy
         of group g-1 overlap the kernels of group g on three streams with two device slots.  The
         current stream is joined at the end (but not synchronised with the host).  Small groups keep
-        the fill and drain of the pipeline short (measured on B200, 64 x 3-min stems: 2 clips per group
-        271 k audio-s/s, 4: 269 k, 8: 259 k, 16: 235 k; the PCIe bound is 315 k).
+        the fill and drain of the pipeline short, but every group costs a set of launches; the default
+        schedule is one clip first (the only copy nothing overlaps), then pairs -- with an even number of
+        clips the last group is a single clip again, which shortens the drain.  Measured on B200, 64 x 3-min
+        stems, one box: (1, 2) 280.5 k audio-s/s, 2 clips per group 271.8 k, 1: 266 k, 4: 269.8 k, 8: 258 k;
+        a third slot changes nothing (tools/e2e_sweep.py).
         """
-        pipe = self._pipeline(lengths, group_clips)
+        pipe = self._pipeline(lengths, group_clips, n_slots)
         if host_in.shape[0] != pipe["total_samples"] or tuple(host_out.shape) != (pipe["total_rows"], self.width):
             raise ValueError("host_in / host_out shapes do not match `lengths`")
         cur = torch.cuda.current_stream(self.device)
@@ -457,10 +471,10 @@ class FrontEnd:
         h2d, comp, d2h = pipe["h2d"], pipe["comp"], pipe["d2h"]
         for s in (h2d, comp, d2h):
             s.wait_event(start)
-        ev_comp = [None, None]   # last compute on each slot (input slot free for the next H2D)
-        ev_d2h = [None, None]    # last D2H on each slot (output slot free for the next compute)
+        ev_comp = [None] * n_slots   # last compute on each slot (input slot free for the next H2D)
+        ev_d2h = [None] * n_slots    # last D2H on each slot (output slot free for the next compute)
         for gi, g in enumerate(pipe["groups"]):
-            slot = gi & 1
+            slot = gi % n_slots
             buf = pipe["slots"][slot]
             if ev_comp[slot] is not None:
                 h2d.wait_event(ev_comp[slot])

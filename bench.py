@@ -207,10 +207,11 @@ def pcie_bandwidth(dev, in_bytes, out_bytes):
         cur.wait_event(e1)
         cur.wait_event(e2)
 
-    ms_h2d = timed(lambda: di.copy_(hi, non_blocking=True))
-    ms_d2h = timed(lambda: ho.copy_(do, non_blocking=True))
-    ms_both = timed(both)
-    return {"h2d_gbs": in_bytes / ms_h2d / 1e6, "d2h_gbs": out_bytes / ms_d2h / 1e6, "both_directions_ms": ms_both}
+    ms_h2d = min(timed(lambda: di.copy_(hi, non_blocking=True)) for _ in range(2))
+    ms_d2h = min(timed(lambda: ho.copy_(do, non_blocking=True)) for _ in range(2))
+    ms_both = min(timed(both) for _ in range(3))
+    return {"h2d_gbs": in_bytes / ms_h2d / 1e6, "d2h_gbs": out_bytes / ms_d2h / 1e6, "h2d_ms": ms_h2d, "d2h_ms": ms_d2h,
+            "both_directions_ms": ms_both}
 
 
 def run_ours(args, rank, world, local_rank):
@@ -338,8 +339,11 @@ def run_ours(args, rank, world, local_rank):
         if rank == 0:
             pc = pcie_bandwidth(dev, int(in_bytes), int(out_bytes))
             e2e["pcie"] = pc
-            # the step cannot be faster than moving its input in and its output out at the same time
-            e2e["pcie_bound_value"] = world * audio_seconds / (pc["both_directions_ms"] * 1e-3)
+            # strict bound: the step cannot be faster than its larger one-direction copy running alone;
+            # reference point: ONE copy of each direction started together (best of three) -- the pipeline's
+            # chunked copies interleave at least as well, so e2e can land slightly above it
+            e2e["pcie_bound_value"] = world * audio_seconds / (max(pc["h2d_ms"], pc["d2h_ms"]) * 1e-3)
+            e2e["pcie_concurrent_value"] = world * audio_seconds / (pc["both_directions_ms"] * 1e-3)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

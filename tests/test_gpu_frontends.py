@@ -207,9 +207,15 @@ def test_pinned_pipeline_equals_resident_path(b2):
     want = fe.run_packed(packed).cpu()
     host_in = torch.from_numpy(np.concatenate(xs)).pin_memory()
     host_out = torch.empty(want.shape, dtype=torch.float32).pin_memory()
-    fe.process_batch_pinned(host_in, lens, host_out, group_clips=2)
-    torch.cuda.synchronize()
-    assert torch.equal(host_out, want)
+    # uniform groups, the default schedule (one clip, then pairs), an explicit schedule, three slots
+    for kw in (dict(group_clips=2), dict(), dict(group_clips=[3, 1, 2]), dict(group_clips=[1, 2], n_slots=3),
+               dict(group_clips=16)):
+        host_out.zero_()
+        fe.process_batch_pinned(host_in, lens, host_out, **kw)
+        torch.cuda.synchronize()
+        assert torch.equal(host_out, want), kw
+    with pytest.raises(ValueError):
+        fe.process_batch_pinned(host_in, lens, host_out, group_clips=[2, 0])
 
 
 def test_device_resident_signal_and_tensor_output(b2):

@@ -17,14 +17,16 @@ host_in = torch.empty(sig.shape, dtype=sig.dtype, pin_memory=True); host_in.copy
 T = 18000 * NC
 host_out = torch.empty((T, fe.width), dtype=torch.float32, pin_memory=True)
 lens = [n] * NC
-for gc in (2, 4, 8, 16, 32):
-    for _ in range(2):
-        fe.process_batch_pinned(host_in, lens, host_out, group_clips=gc)
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(5):
-        fe.process_batch_pinned(host_in, lens, host_out, group_clips=gc)
-    b.record(); torch.cuda.synchronize()
-    ms = a.elapsed_time(b) / 5
-    print(json.dumps({"group_clips": gc, "ms_per_step": ms, "audio_s_per_s": NC * SEC / ms * 1e3}), flush=True)
+CASES = [(2, 2), ([1, 2], 2), (1, 2), (2, 3), ([1, 2], 3), (4, 2), (8, 2)]
+for rep in range(2):
+    for gc, ns in CASES:
+        for _ in range(2):
+            fe.process_batch_pinned(host_in, lens, host_out, group_clips=gc, n_slots=ns)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            fe.process_batch_pinned(host_in, lens, host_out, group_clips=gc, n_slots=ns)
+        b.record(); torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 5
+        print(json.dumps({"group_clips": gc, "slots": ns, "ms_per_step": round(ms, 3), "audio_s_per_s": round(NC * SEC / ms * 1e3)}), flush=True)
