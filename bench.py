@@ -13,8 +13,9 @@ max-over-ranks device time.
 
 Prints ONE JSON line (rank 0).  `value` is device-resident throughput; `e2e` is the same metric
 through FrontEnd.process_batch_pinned (pinned host buffers in, pinned host buffers out, copies
-inside the timed region); `roofline` is for the dominant kernel (frame 4096) timed alone with CUDA
-events; `cpu_baseline` times the numpy oracle (madmom restatement) on the host cores.
+inside the timed region; `e2e.pcie_bound_value` = what the larger one-direction copy of the step alone
+allows, `e2e.pcie_concurrent_value` = one H2D and one D2H copy of the step's bytes started together);
+`roofline` is for the dominant kernel (frame 4096), CUDA events around every launch of the timed region; `cpu_baseline` times the numpy oracle (madmom restatement) on the host cores.
 """
 from __future__ import annotations
 
