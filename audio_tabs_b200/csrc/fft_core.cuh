@@ -445,21 +445,41 @@ B2_HD void fft_pair_pass3_unit(int u, const float2 *pa, const float2 *pb, const 
 // The self-paired column q = 128 (bins 128 + 256 j), lane-parallel on R3 lanes of one warp:
 // lane k3 forms Z[128 + 256 k3] = sum_n c[n] W_(2 R3)^(n (2 k3 + 1)); the caller exchanges Z with lane
 // R3-1-k3 (the mirror bin) and emits |Z + conj Z'| (frame A) and |Z - conj Z'| (frame B) for k3 < R3/2.
+// The sum is cut into kCol128Parts<F2> parts of consecutive terms so that the kernel can spread it over
+// R3 * parts lanes (part = lane / R3) and add the parts with xor shuffles: the warp that owns column 128 is
+// the last one to reach the barrier after pass 3, and this is the extra work it does.  Measured on B200: two
+// parts at R3 = 16 (frame 4096 of the pair kernel) 6.76 -> 6.71 ms; four parts at R3 = 8 / 4 LOSE 2.4 % / 1.2 %
+// (the sums are short there and the shuffles cost more than they save), so those stay on one lane per bin.
 template <int F2>
-B2_HD float2 fft_pair_col128(int k3, const float2 *buf, const float2 *wr) {
+constexpr int kCol128Parts = FftCfg<F2>::R3 >= 16 ? 2 : 1;
+
+template <int F2>
+B2_HD float2 fft_pair_col128_part(int k3, int part, const float2 *buf, const float2 *wr) {
   using C = FftCfg<F2>;
-  constexpr int R3 = C::R3;
-  const float2 *c = buf + fft_col_offset<F2>(128);
+  constexpr int R3 = C::R3, TPP = R3 / kCol128Parts<F2>;   // terms per part
+  static_assert(TPP >= 1, "more parts than terms");
+  const float2 *c = buf + fft_col_offset<F2>(128) + part * TPP;
   const int step = 2 * k3 + 1;
-  int e = 0;
+  int e = (part * TPP * step) & (2 * R3 - 1);
   float2 Z = make_float2(0.f, 0.f);
 #pragma unroll
-  for (int n = 0; n < R3; ++n) {
+  for (int n = 0; n < TPP; ++n) {
     const float2 w = wr[e];
     const float2 cn = c[n];
     Z.x = fmaf(w.x, cn.x, fmaf(-w.y, cn.y, Z.x));
     Z.y = fmaf(w.x, cn.y, fmaf(w.y, cn.x, Z.y));
     e = (e + step) & (2 * R3 - 1);
+  }
+  return Z;
+}
+
+template <int F2>
+B2_HD float2 fft_pair_col128(int k3, const float2 *buf, const float2 *wr) {   // all parts on one lane (tests/emu)
+  float2 Z = make_float2(0.f, 0.f);
+  for (int part = 0; part < kCol128Parts<F2>; ++part) {
+    const float2 z = fft_pair_col128_part<F2>(k3, part, buf, wr);
+    Z.x += z.x;
+    Z.y += z.y;
   }
   return Z;
 }

@@ -323,7 +323,14 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front_pair(const FrontP
                                   [&](int bin, float2 xa, float2 xb) { put(bin, cabs_fast(xa), cabs_fast(xb)); });
           if (tid < 32) {          // the self-paired column 128: one bin per lane, mirror bin by shuffle
             const int k3 = tid & (R3 - 1);
-            const float2 Z = fft_pair_col128<F2>(k3, fbuf, s_wr);
+            constexpr int NPART = kCol128Parts<F2>;                     // R3 * NPART <= 32 lanes share the sum
+            float2 Z = make_float2(0.f, 0.f);
+            if (tid < R3 * NPART) Z = fft_pair_col128_part<F2>(k3, tid / R3, fbuf, s_wr);
+#pragma unroll
+            for (int d = R3; d < R3 * NPART; d <<= 1) {
+              Z.x += __shfl_xor_sync(0xffffffffu, Z.x, d);
+              Z.y += __shfl_xor_sync(0xffffffffu, Z.y, d);
+            }
             const float zx = __shfl_sync(0xffffffffu, Z.x, R3 - 1 - k3), zy = __shfl_sync(0xffffffffu, Z.y, R3 - 1 - k3);
             if (tid < R3 / 2)       // |Z + conj Z'| (frame A), |Z - conj Z'| (frame B)
               put(128 + 256 * tid, cabs_fast(make_float2(Z.x + zx, Z.y - zy)), cabs_fast(make_float2(Z.x - zx, Z.y + zy)));
