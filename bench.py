@@ -28,6 +28,14 @@ import tempfile
 import time
 from pathlib import Path
 
+# The CPU legs run ONE single-threaded worker process per host core (how the reference scales: one Celery
+# worker per job).  The BLAS / OpenMP pools must be capped BEFORE numpy is first imported -- a forked
+# worker inherits the parent's already-initialised OpenBLAS pool, and a later os.environ change does
+# nothing (round 1 measured 16 workers x 16 BLAS threads: ~6x too slow a baseline).  The GPU arm does
+# no host arithmetic, so the cap costs it nothing.
+for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+    os.environ[_v] = "1"
+
 import numpy as np
 
 ROOT = Path(__file__).resolve().parent
@@ -43,53 +51,96 @@ WORKLOAD = "64 x 180 s 44.1 kHz mono f32 stems, frames 1024/2048/4096 hop 441, 3
 # ------------------------------------------------------------------------------------------------
 # CPU baseline / reference arm: the oracle (numpy restatement of madmom 0.16.1) on the host cores
 # ------------------------------------------------------------------------------------------------
-def _cpu_worker(args):
+_CPU_CLIPS = {}      # (seed, seconds) -> synthetic guitar clip; filled in the parent BEFORE the timed pool forks
+
+
+def _blas_threads(_=None):
+    """threads of the BLAS / OpenMP pools loaded in this process (1 each is what the baseline wants)"""
+    try:
+        from threadpoolctl import threadpool_info
+        return sorted({int(i.get("num_threads", 0)) for i in threadpool_info()}) or [1]
+    except Exception:
+        return None
+
+
+def _cpu_synth(args):
     seed, seconds = args
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    from audio_tabs_b200.synth import synth_guitar
+    return synth_guitar(seed, seconds)
+
+
+def _cpu_worker(args):
     from oracle import madmom_ref as ref
-    rng = np.random.default_rng(seed)
-    x = (rng.standard_normal(int(seconds * SR)) * 0.1).astype(np.float32)
+    x = _CPU_CLIPS[args]
     out = ref.rnn_beat_preprocessor()(x)
     return out.shape[0]
 
 
-def cpu_front_end_throughput(clip_seconds=20.0, clips_per_core=2, cores=None):
-    """audio-s/s of the oracle with one worker process per host core (how the reference scales:
-    one Celery worker per job, /root/reference/docker-compose.yml:28)."""
+def cpu_front_end_throughput(clip_seconds=30.0, clips_per_core=4, cores=None):
+    """audio-s/s of the oracle (madmom restatement: per-frame scipy.fftpack.fft loop, float32 filterbank dot,
+    log10, difference, hstack -- the three resolutions of RNNBeatProcessor) on synthetic guitar clips
+    (SURVEY.md section 8d generator, seed = 2000 + i as for config 2), one single-threaded worker process per
+    host core (how the reference scales: one Celery worker per job, /root/reference/docker-compose.yml:28).
+    Audio-s/s does not depend on the clip length on this path, so the sample is `clips_per_core` clips of
+    `clip_seconds` per core instead of the 64 x 180 s of the GPU arm.  Clip synthesis is outside the timed
+    region (the clips are made first and inherited by the forked workers)."""
     import multiprocessing as mp
-    cores = cores or os.cpu_count() or 1
-    jobs = [(1000 + i, clip_seconds) for i in range(cores * clips_per_core)]
+    cores = cores or len(os.sched_getaffinity(0)) or os.cpu_count() or 1
+    jobs = [(2000 + i, float(clip_seconds)) for i in range(cores * clips_per_core)]
     ctx = mp.get_context("fork")
-    with ctx.Pool(cores) as pool:
-        pool.map(_cpu_worker, [(0, 1.0)] * cores)        # spin up workers, import numpy/scipy
+    todo = [j for j in jobs + [(0, 1.0)] if j not in _CPU_CLIPS]
+    if todo:
+        with ctx.Pool(cores) as pool:                    # untimed: synthesise the clips in parallel (kept across steps)
+            for j, x in zip(todo, pool.map(_cpu_synth, todo, chunksize=1)):
+                _CPU_CLIPS[j] = x
+    with ctx.Pool(cores) as pool:                        # forked now: the workers see _CPU_CLIPS
+        pool.map(_cpu_worker, [(0, 1.0)] * cores)        # spin up workers, import scipy, build the filterbanks
+        blas = pool.map(_blas_threads, range(cores))[0]
         t0 = time.perf_counter()
         pool.map(_cpu_worker, jobs, chunksize=1)
         dt = time.perf_counter() - t0
     audio = clip_seconds * len(jobs)
-    return audio / dt, cores, "%d clips x %.0f s white noise, %d worker processes" % (len(jobs), clip_seconds, cores), dt
+    info = {"cores": cores, "blas_threads_per_worker": blas, "workers": cores,
+            "sample": "%d synthetic guitar clips x %.0f s (same generator and front end as the GPU arm), %d single-threaded "
+                      "worker processes" % (len(jobs), clip_seconds, cores)}
+    return audio / dt, info, dt
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    for _ in range(args.warmup if args.warmup < 1 else 1):
+    for _ in range(min(args.warmup, 1)):
         cpu_front_end_throughput(clip_seconds=5.0, clips_per_core=1)
     vals, dts = [], []
     for _ in range(args.steps):
-        v, cores, sample, dt = cpu_front_end_throughput(clip_seconds=20.0, clips_per_core=2)
+        v, info, dt = cpu_front_end_throughput()
         vals.append(v)
         dts.append(dt)
     value = float(np.mean(vals))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(dts)),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 FFT / f32 spectrogram",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "note": "CPU oracle port of madmom 0.16.1 (madmom itself is not installable offline); bounded sample per step"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": bench_config(N_CLIPS, CLIP_SECONDS, args.gpus),
+        "reference_note": "CPU oracle port of madmom 0.16.1 (madmom itself is not installable offline); computes f64 FFT / "
+                          "f32 spectrogram like madmom; each step is a bounded sample of the workload: " + info["sample"],
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": "port", "sample": info["sample"],
+                         "blas_threads_per_worker": info["blas_threads_per_worker"],
+                         "per_core": value / info["cores"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def bench_config(n_clips, clip_seconds, world):
+    """the `config` object both arms print (same keys, same values for the same workload)"""
+    full = (n_clips, clip_seconds) == (N_CLIPS, CLIP_SECONDS)
+    in_gb = n_clips * clip_seconds * SR * 4 / 1e9
+    out_gb = n_clips * int(np.ceil(clip_seconds * SR / 441.0)) * 314 * 4 / 1e9
+    return {"workload": WORKLOAD if full else "%d x %.0f s stems (reduced)" % (n_clips, clip_seconds),
+            "clips_per_gpu": n_clips, "clip_seconds": clip_seconds, "parallelism": "job-sharded x%d" % world,
+            "l2": "inputs (%.2f GB) + outputs (%.2f GB) per step exceed the 126 MB L2" % (in_gb, out_gb)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -348,18 +399,16 @@ def run_ours(args, rank, world, local_rank):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        v, cores, sample, dt = cpu_front_end_throughput(clip_seconds=20.0, clips_per_core=2)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "seconds": dt}
+        v, info, dt = cpu_front_end_throughput()
+        cpu = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": "port", "sample": info["sample"], "seconds": dt,
+               "blas_threads_per_worker": info["blas_threads_per_worker"], "per_core": v / info["cores"]}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD if (n_clips, args.clip_seconds) == (N_CLIPS, CLIP_SECONDS) else
-                       "%d x %.0f s stems (reduced)" % (n_clips, args.clip_seconds),
-                       "clips_per_gpu": n_clips, "clip_seconds": args.clip_seconds, "parallelism": "job-sharded x%d" % world,
-                       "l2": "inputs (%.2f GB) + outputs (%.2f GB) per step exceed the 126 MB L2" % (in_bytes / 1e9, out_bytes / 1e9)},
+            "config": bench_config(n_clips, args.clip_seconds, world),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
