@@ -9,12 +9,13 @@ import ctypes as C
 import os
 from pathlib import Path
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_RES = 4
 MAX_DIFF_FRAMES = 16
 
 OK, ERR_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_ARCH = 0, -1, -2, -3, -4
 F32, I16 = 0, 1
+CLIP_NONFINITE = 1
 END_NORMAL, END_EXTEND = 0, 1
 
 c_float_p = C.POINTER(C.c_float)
@@ -69,6 +70,7 @@ class OutDesc(C.Structure):
         ("d_proj", C.c_void_p),
         ("ld_proj", C.c_int64),
         ("d_clip_scale", C.c_void_p),
+        ("d_clip_status", C.c_void_p),
     ]
 
 

@@ -51,6 +51,10 @@ class Signal(np.ndarray):
                 gain=0.0, dtype=None, **kwargs):
         if isinstance(data, (str, bytes)) or hasattr(data, "read"):
             data, file_rate = _load_wave(data, dtype=dtype)
+            if start is not None or stop is not None:       # seconds, as madmom.io.audio.load_wave_file cuts them
+                lo = 0 if start is None else int(start * file_rate)
+                hi = len(data) if stop is None else min(len(data), int(stop * file_rate))
+                data = data[lo:hi]
             if sample_rate is not None and sample_rate != file_rate:
                 raise NotImplementedError("resampling needs ffmpeg, which the reference does before this "
                                           "path (services/audio.py:7-16)")
@@ -110,6 +114,16 @@ class SignalProcessor(Processor):
         args = dict(sample_rate=self.sample_rate, num_channels=self.num_channels, start=self.start,
                     stop=self.stop, norm=self.norm, gain=self.gain, dtype=self.dtype)
         args.update(kwargs)
+        if _is_tensor(data) or isinstance(data, DeviceSignal):
+            # device-resident samples are never rewritten: the options that would need a pass over them raise
+            # instead of being dropped (norm is the exception: it is fused as a per-clip gain)
+            if args["gain"] not in (None, 0, 0.0):
+                raise NotImplementedError("gain != 0 is not implemented for device-resident signals")
+            if args["start"] is not None or args["stop"] is not None:
+                raise NotImplementedError("start / stop are not implemented for device-resident signals; slice the tensor")
+            if args["dtype"] is not None and np.dtype(args["dtype"]) != (data.dtype if isinstance(data, DeviceSignal)
+                                                                         else np.dtype(str(data.dtype).replace("torch.", ""))):
+                raise NotImplementedError("dtype conversion is not implemented for device-resident signals")
         if _is_tensor(data):
             return DeviceSignal(data, sample_rate=args["sample_rate"], num_channels=args["num_channels"],
                                 norm=args["norm"])
@@ -132,8 +146,9 @@ class DeviceSignal:
         self.data = remix(data, num_channels)
         self.sample_rate = sample_rate
         # madmom Signal(norm=True) divides by max|x|.  The samples are not rewritten: the fused chains
-        # apply 1 / max|x| (b200spec_clip_peak) as a gain on the band sums, which is the same thing
-        # because the path is linear up to the logarithm.
+        # apply g = 1 / max|x| (b200spec_clip_peak) as a gain on the band sums -- g for a magnitude
+        # spectrogram, g^2 for a power spectrogram (the kernel squares it) -- which is the same thing
+        # because the path is linear in the samples up to the magnitude.
         self.norm = bool(norm)
 
     def __len__(self):

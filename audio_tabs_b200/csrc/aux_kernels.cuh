@@ -32,17 +32,18 @@ __global__ void k_setup_tasks(const long long *__restrict__ frame_off, int n_cli
 }
 
 // ---- per-clip peak: max |x| of the down-mixed samples ------------------------------------------------
-// grid = (kPeakBlocksPerClip, n_clips); the clip's samples are strided over its blocks; |x| >= 0 so the
+// grid = kPeakBlocksPerClip * n_clips blocks (clip = blockIdx.x / kPeakBlocksPerClip: no 65535 limit of
+// grid.y); the clip's samples are strided over its blocks; |x| >= 0 so the
 // float bit pattern orders like an unsigned integer and atomicMax on it is exact.
 constexpr int kPeakBlocksPerClip = 32;
 template <int IN>
 __global__ void k_clip_peak(const void *__restrict__ sig, const long long *__restrict__ clip_off,
                             unsigned int *__restrict__ peak_bits) {
-  const int c = blockIdx.y;
+  const int c = blockIdx.x / kPeakBlocksPerClip, part = blockIdx.x % kPeakBlocksPerClip;
   const long long s0 = clip_off[c], n = clip_off[c + 1] - s0;
   Samples<IN> S{clip_base<IN>(sig, s0)};
   float m = 0.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+  for (long long i = part * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)kPeakBlocksPerClip * blockDim.x)
     m = fmaxf(m, fabsf(S.at(i)));
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
@@ -63,8 +64,8 @@ __global__ void k_peak_reciprocal(float *__restrict__ peak, int n, float eps, fl
 }
 
 // ---- onset-strength envelope (librosa.onset.onset_strength on rows of a (T, B) matrix) ------------------
-// maximum of each clip's rows (power_to_db's top_db clip is relative to it): grid = (kRowmaxBlocksPerClip,
-// n_clips), one warp per row at a time, block result merged with an ordered-float atomic max.
+// maximum of each clip's rows (power_to_db's top_db clip is relative to it): grid = kRowmaxBlocksPerClip *
+// n_clips blocks, one warp per row at a time, block result merged with an ordered-float atomic max.
 // clip_max must hold -inf on entry (k_fill_neg_inf).
 constexpr int kRowmaxBlocksPerClip = 16;
 __global__ void k_fill_neg_inf(float *__restrict__ x, int n) {
@@ -77,11 +78,11 @@ __device__ __forceinline__ void atomic_max_float(float *addr, float v) {
 }
 __global__ void k_clip_rowmax(const float *__restrict__ L, long long ld_L, int B, const long long *__restrict__ frame_off,
                               float *__restrict__ clip_max) {
-  const int c = blockIdx.y;
+  const int c = blockIdx.x / kRowmaxBlocksPerClip, part = blockIdx.x % kRowmaxBlocksPerClip;
   const long long r0 = frame_off[c], rows = frame_off[c + 1] - r0;
   const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   float m = -INFINITY;
-  for (long long r = blockIdx.x * nw + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * nw) {
+  for (long long r = part * nw + (threadIdx.x >> 5); r < rows; r += (long long)kRowmaxBlocksPerClip * nw) {
     const float *x = L + (r0 + r) * ld_L;
     for (int j = lane; j < B; j += 32) m = fmaxf(m, x[j]);
   }

@@ -12,6 +12,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "aux_kernels.cuh"
 #include "fb_pack.h"
 #include "front_inst.cuh"
@@ -54,6 +56,23 @@ struct DeviceGuard {
     if (switched) cudaSetDevice(prev);
   }
 };
+
+// NVTX range around a launch sequence (header-only NVTX v3: costs one indirect call unless a tool is attached)
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
+// the device that owns a device pointer, and its SM count (entry points without a plan)
+int pointer_device(const void *p, int *device, int *num_sms) {
+  cudaPointerAttributes at;
+  CU_CHECK(cudaPointerGetAttributes(&at, p));
+  if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)
+    return fail(B200SPEC_ERR_ARG, "pointer %p is not device memory", p);
+  *device = at.device;
+  CU_CHECK(cudaDeviceGetAttribute(num_sms, cudaDevAttrMultiProcessorCount, at.device));
+  return 0;
+}
 
 struct ResPlan {
   int frame_size = 0;
@@ -101,12 +120,12 @@ namespace {
 template <class T>
 int upload(b200spec_plan *pl, const T *host, size_t n, T **out) {
   *out = nullptr;
-  if (n == 0) n = 1;  // keep pointers valid
+  const size_t alloc_n = n == 0 ? 1 : n;  // keep pointers valid
   void *d = nullptr;
-  CU_CHECK(cudaMalloc(&d, n * sizeof(T)));
+  CU_CHECK(cudaMalloc(&d, alloc_n * sizeof(T)));
   pl->allocs.push_back(d);
-  if (host) CU_CHECK(cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice));
-  else CU_CHECK(cudaMemset(d, 0, n * sizeof(T)));
+  if (host && n > 0) CU_CHECK(cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice));
+  else CU_CHECK(cudaMemset(d, 0, alloc_n * sizeof(T)));   // nothing is read from a zero-length host array
   *out = reinterpret_cast<T *>(d);
   return 0;
 }
@@ -138,6 +157,13 @@ int build_res(b200spec_plan *pl, const b200spec_res_desc &d, ResPlan &r) {
   r.diff_max_bins = d.diff_max_bins > 1 ? d.diff_max_bins : 0;
   r.num_bands = d.num_bands;
   r.num_classes = d.num_classes;
+  if (d.num_classes > 0) {   // validated before anything reads proj_off (the shared-memory probe below does)
+    if (!d.proj_off || !d.proj_band || !d.proj_weight) return fail(B200SPEC_ERR_ARG, "projection arrays are NULL");
+    if (d.proj_off[0] != 0) return fail(B200SPEC_ERR_ARG, "proj_off[0] must be 0");
+    for (int c = 0; c < d.num_classes; ++c)
+      if (d.proj_off[c + 1] < d.proj_off[c]) return fail(B200SPEC_ERR_ARG, "proj_off must be non-decreasing");
+    if (d.proj_off[d.num_classes] > (1 << 20)) return fail(B200SPEC_ERR_ARG, "projection has too many entries");
+  }
 
   // window: the real frame is packed as z[m] = x[2m] + i x[2m+1]; the 1/2 of the even/odd split
   // E = (Z[k] + conj(Z[N-k])) / 2 is folded into the window (exact in binary floating point)
@@ -196,8 +222,13 @@ int build_res(b200spec_plan *pl, const b200spec_res_desc &d, ResPlan &r) {
     const double sc = sw / shh;
     double dev = 0.0;
     for (int i = 0; i < F; ++i) dev = std::max(dev, fabs((double)d.window[i] - sc * hann[i]));
+#ifdef B200SPEC_TUNING   // A/B knob of tuning builds only (-DB200SPEC_TUNING); the product build reads no environment
     const char *wf = getenv("B200SPEC_WINFLY");
-    if (sc > 0.0 && dev <= 1.5e-7 * sc && !(wf && wf[0] == '0')) {
+    const bool winfly_on = !(wf && wf[0] == '0');
+#else
+    const bool winfly_on = true;
+#endif
+    if (sc > 0.0 && dev <= 1.5e-7 * sc && winfly_on) {
       const int bpf = F / 16;
       const double H = 0.25 * sc;
       r.win_fly = 1;
@@ -251,8 +282,10 @@ int build_res(b200spec_plan *pl, const b200spec_res_desc &d, ResPlan &r) {
       case 4096: need = b2::front_smem_layout<4096>(probe, b2::MODE_LOGFILT, b2::GroupsPerCta<4096>::value); break;
       default: need = b2::front_smem_layout<8192>(probe, b2::MODE_LOGFILT, b2::GroupsPerCta<8192>::value); break;
     }
+#ifdef B200SPEC_TUNING
     if (const char *e = getenv("B200SPEC_W4_GLOBAL"))   // tuning override: force the global-memory table
       if (e[0] == '1') need = b2::kMaxSmemPerCta + 1;
+#endif
     if (need > b2::kMaxSmemPerCta) {   // keep the table in global memory (one fixed slab length)
       fp = b2::fb_pack(N, B, d.band_start, d.band_len, d.band_woff, d.weights, TBF, 15);
       r.fb_w4_global = 1;
@@ -273,7 +306,6 @@ int build_res(b200spec_plan *pl, const b200spec_res_desc &d, ResPlan &r) {
   if ((rc = upload(pl, d.band_woff, (size_t)B, &r.d_band_woff))) return rc;
 
   if (d.num_classes > 0) {
-    if (!d.proj_off || !d.proj_band || !d.proj_weight) return fail(B200SPEC_ERR_ARG, "projection arrays are NULL");
     const int np = d.proj_off[d.num_classes];
     r.nproj = np;
     for (int i = 0; i < np; ++i)
@@ -308,10 +340,12 @@ int choose_chunk(const b200spec_plan *pl, int F, long long total_frames, int kd)
   // a task transforms chunk + kd frames (kd warm-up rows of the difference); keep that a multiple of the
   // tail batch (4 frames, pairs of frames in k_front_pair) so no step runs half empty
   if (chunk >= 16) chunk -= (chunk + kd) % 4;
+#ifdef B200SPEC_TUNING
   if (const char *e = getenv("B200SPEC_CHUNK")) {   // tuning override
     const int v = atoi(e);
     if (v > 0) chunk = v;
   }
+#endif
   return (int)chunk;
 }
 
@@ -330,6 +364,10 @@ int launch_front(const b200spec_plan *pl, int res, int mode, const void *d_sig, 
   DeviceGuard guard;
   CU_CHECK(guard.enter(pl->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static const char *const kRangeNames[2][4] = {
+      {"b200spec front end 1024", "b200spec front end 2048", "b200spec front end 4096", "b200spec front end 8192"},
+      {"b200spec stft 1024", "b200spec stft 2048", "b200spec stft 4096", "b200spec stft 8192"}};
+  NvtxRange range(kRangeNames[mode == b2::MODE_LOGFILT ? 0 : 1][r.frame_size == 1024 ? 0 : r.frame_size == 2048 ? 1 : r.frame_size == 4096 ? 2 : 3]);
 
   const int chunk = choose_chunk(pl, r.frame_size, total_frames, mode == b2::MODE_LOGFILT ? r.diff_frames : 0);
   b2::k_setup_tasks<<<1, 1024, 0, st>>>(reinterpret_cast<const long long *>(d_frame_off), n_clips, chunk,
@@ -385,7 +423,11 @@ int launch_front(const b200spec_plan *pl, int res, int mode, const void *d_sig, 
   // The log-filtered path of frames <= 4096 runs the pair kernel (two frames per complex FFT);
   // B200SPEC_PAIR=0 keeps the one-frame kernel (A/B measurements), as does a configuration whose
   // tables do not fit next to the larger FFT buffer.
+#ifdef B200SPEC_TUNING
   static const bool use_pair = []() { const char *v = getenv("B200SPEC_PAIR"); return !(v && v[0] == '0'); }();
+#else
+  constexpr bool use_pair = true;
+#endif
   if (use_pair && mode == b2::MODE_LOGFILT && r.frame_size <= 4096 && r.d_pair_tw3 != nullptr) {
     b2::FrontParams q = p;
     q.tw3 = r.d_pair_tw3;
@@ -534,6 +576,7 @@ int b200spec_logfilt(const b200spec_plan *plan, int32_t res, const void *d_sig, 
   p.col_diff = out->col_diff;
   p.flux = out->d_flux;
   p.clip_scale = out->d_clip_scale;
+  p.clip_status = out->d_clip_status;
   p.proj = out->d_proj;
   p.ld_proj = out->ld_proj;
   p.num_classes = out->d_proj ? r.num_classes : 0;
@@ -552,7 +595,8 @@ int b200spec_clip_peak(const b200spec_plan *plan, const void *d_sig, const int64
   CU_CHECK(guard.enter(plan->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CU_CHECK(cudaMemsetAsync(d_peak, 0, sizeof(float) * (size_t)n_clips, st));
-  const dim3 grid(b2::kPeakBlocksPerClip, (unsigned)n_clips);
+  if ((long long)n_clips * b2::kPeakBlocksPerClip > 0x7fffffffLL) return fail(B200SPEC_ERR_ARG, "too many clips");
+  const unsigned grid = (unsigned)n_clips * b2::kPeakBlocksPerClip;
   const long long *co = reinterpret_cast<const long long *>(d_clip_off);
   unsigned int *bits = reinterpret_cast<unsigned int *>(d_peak);
   switch ((plan->dtype == B200SPEC_I16 ? 2 : 0) + (plan->channels == 2 ? 1 : 0)) {
@@ -579,8 +623,13 @@ int b200spec_context_stack(const float *d_in, int64_t ld_in, int32_t num_bands, 
   if (n_clips == 0 || total_frames == 0) return 0;
   if (!d_in || !d_frame_off || !d_out) return fail(B200SPEC_ERR_ARG, "NULL device pointer");
   if (num_bands < 1 || ld_in < num_bands || context < 1) return fail(B200SPEC_ERR_ARG, "num_bands / ld_in / context out of range");
+  int dev = 0, sms = 0, rc = pointer_device(d_in, &dev, &sms);   // no plan here: launch on the device that owns d_in
+  if (rc) return rc;
+  DeviceGuard guard;
+  CU_CHECK(guard.enter(dev));
+  NvtxRange range("b200spec context stack");
   long long blocks = (total_frames + 7) / 8;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > sms * 16) blocks = sms * 16;
   b2::k_context_stack<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       d_in, ld_in, num_bands, reinterpret_cast<const long long *>(d_frame_off), n_clips, total_frames, context, d_out);
   CU_CHECK(cudaGetLastError());
@@ -597,14 +646,20 @@ int b200spec_onset_envelope(const float *d_L, int64_t ld_L, int32_t num_bands, c
   if (num_bands < 1 || num_bands > 1024 || ld_L < num_bands) return fail(B200SPEC_ERR_ARG, "num_bands outside [1, 1024] or ld_L < num_bands");
   if (lag < 1 || shift < 0) return fail(B200SPEC_ERR_ARG, "lag must be >= 1 and shift >= 0");
   if (aggregate != 0 && aggregate != 1) return fail(B200SPEC_ERR_ARG, "aggregate must be 0 (mean) or 1 (median)");
+  if ((long long)n_clips * b2::kRowmaxBlocksPerClip > 0x7fffffffLL) return fail(B200SPEC_ERR_ARG, "too many clips");
+  int dev = 0, sms = 0, rc = pointer_device(d_L, &dev, &sms);    // no plan here: launch on the device that owns d_L
+  if (rc) return rc;
+  DeviceGuard guard;
+  CU_CHECK(guard.enter(dev));
+  NvtxRange range("b200spec onset envelope");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long long *fo = reinterpret_cast<const long long *>(d_frame_off);
   b2::k_fill_neg_inf<<<(n_clips + 255) / 256, 256, 0, st>>>(d_clip_max, n_clips);
-  b2::k_clip_rowmax<<<dim3(b2::kRowmaxBlocksPerClip, (unsigned)n_clips), 256, 0, st>>>(d_L, ld_L, num_bands, fo, d_clip_max);
+  b2::k_clip_rowmax<<<(unsigned)n_clips * b2::kRowmaxBlocksPerClip, 256, 0, st>>>(d_L, ld_L, num_bands, fo, d_clip_max);
   CU_CHECK(cudaGetLastError());
   g_launches += 2;
   long long blocks = (total_frames + 7) / 8;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > sms * 16) blocks = sms * 16;
   // rows of up to 256 bands are sorted in registers (1, 2, 4 or 8 values per lane); wider ones go through shared memory
   const int per_lane = (num_bands + 31) / 32;
 #define B2_ONSET_ARGS d_L, ld_L, num_bands, fo, n_clips, total_frames, lag, top_db, aggregate, shift, d_clip_max, d_env
@@ -623,8 +678,12 @@ int b200spec_magnitude(const float *d_stft, int64_t n_elems, float *d_out, void 
   if (n_elems < 0) return fail(B200SPEC_ERR_ARG, "n_elems < 0");
   if (n_elems == 0) return 0;
   if (!d_stft || !d_out) return fail(B200SPEC_ERR_ARG, "NULL device pointer");
+  int dev = 0, sms = 0, rc = pointer_device(d_stft, &dev, &sms);  // no plan here: launch on the device that owns d_stft
+  if (rc) return rc;
+  DeviceGuard guard;
+  CU_CHECK(guard.enter(dev));
   long long blocks = (n_elems + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > sms * 16) blocks = sms * 16;
   b2::k_magnitude<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const float2 *>(d_stft), n_elems, d_out);
   CU_CHECK(cudaGetLastError());

@@ -76,7 +76,8 @@ struct FrontParams {
   long long ld_out;
   int col_spec, col_diff;
   float *flux;
-  const float *clip_scale;   // per-clip gain on the band sums (nullptr = 1)
+  const float *clip_scale;   // per-clip gain on the samples (nullptr = 1): band sums scale with it (its square when power)
+  int *clip_status;          // per-clip status word (nullptr = not wanted): bit 0 = a non-finite output value
   float *proj;
   long long ld_proj;
   // outputs (MODE_SPECTRUM)
@@ -240,7 +241,7 @@ struct TailCtx {
 
 template <int TB, int TBF, class MA>
 __device__ __forceinline__ int front_tail(const FrontParams &p, const TailCtx &c, int fb, int f0, int f1,
-                                          long long row0, int hslot, float cscale) {
+                                          long long row0, int hslot, float cscale, int &nonfinite) {
   const float4 *s_w4 = c.s_w4;
   const int4 *s_band = c.s_band;
   const float *s_dw = c.s_dw;
@@ -326,6 +327,7 @@ __device__ __forceinline__ int front_tail(const FrontParams &p, const TailCtx &c
               if (c.lfloor > 0.f) a = fmaxf(a, c.lfloor);
               L = fast_lg2(a) * c.lk;                               // log_scale * log10(a)
             }
+            nonfinite |= !(fabsf(L) <= 3.402823466e38f);           // NaN or Inf (from NaN / Inf samples)
             float D = 0.f;
             if (kd > 0) {
               const float old = *hp;
@@ -479,7 +481,9 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
     const int f1 = min(T, f0 + p.chunk);
     const int fs = (MODE == MODE_LOGFILT && kd > 0) ? max(0, f0 - kd) : f0;  // warm-up rows for the diff
     Samples<IN> S{clip_base<IN>(p.sig, samp0)};
-    const float cscale = (MODE == MODE_LOGFILT && p.clip_scale != nullptr) ? __ldg(p.clip_scale + c) : 1.f;
+    float cscale = (MODE == MODE_LOGFILT && p.clip_scale != nullptr) ? __ldg(p.clip_scale + c) : 1.f;
+    if (p.power) cscale *= cscale;       // |g x|^2 = g^2 |x|^2: a power spectrogram scales with the gain squared
+    int nonfinite = 0;
 
     int hslot = (MODE == MODE_LOGFILT && kd > 0) ? fs % kd : 0;   // difference ring slot of frame f
     for (int fb = fs; fb < f1; fb += TB) {
@@ -581,8 +585,9 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
         group_bar(g);   // pass-3 reads done: buf is free again; magnitudes visible
       }
       // =============== tail for the TB frames of this batch, TBF at a time ===============
-      if (MODE == MODE_LOGFILT) hslot = front_tail<TB, TBF, MagLinear<MS>>(p, tctx, fb, f0, f1, row0, hslot, cscale);
+      if (MODE == MODE_LOGFILT) hslot = front_tail<TB, TBF, MagLinear<MS>>(p, tctx, fb, f0, f1, row0, hslot, cscale, nonfinite);
     }
+    if (MODE == MODE_LOGFILT && p.clip_status != nullptr && nonfinite) atomicOr(p.clip_status + c, 1);
   }
 }
 

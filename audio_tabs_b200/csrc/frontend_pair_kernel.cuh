@@ -193,7 +193,9 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front_pair(const FrontP
     const int f1 = min(T, f0 + p.chunk);
     const int fs = kd > 0 ? max(0, f0 - kd) : f0;            // warm-up rows for the difference
     Samples<IN> S{clip_base<IN>(p.sig, samp0)};
-    const float cscale = p.clip_scale != nullptr ? __ldg(p.clip_scale + c) : 1.f;
+    float cscale = p.clip_scale != nullptr ? __ldg(p.clip_scale + c) : 1.f;
+    if (p.power) cscale *= cscale;       // a power spectrogram scales with the gain squared
+    int nonfinite = 0;
 
     int hslot = kd > 0 ? fs % kd : 0;                        // difference ring slot of frame fb
     staged = false;                                          // (a task never ends with a copy in flight: fn + FPS <= f1)
@@ -362,9 +364,10 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front_pair(const FrontP
           }
         }
       }
-      hslot = front_tail<TB, TBF, typename P::MA>(p, tctx, fb, f0, f1, row0, hslot, cscale);
+      hslot = front_tail<TB, TBF, typename P::MA>(p, tctx, fb, f0, f1, row0, hslot, cscale, nonfinite);
       if (P::INPLACE) group_bar(g);   // the band stage has read its magnitudes before pass 1 overwrites the buffer
     }
+    if (p.clip_status != nullptr && nonfinite) atomicOr(p.clip_status + c, 1);
   }
 }
 

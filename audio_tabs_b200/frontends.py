@@ -50,7 +50,10 @@ class MultiResolutionFrontEnd(Processor):
             raise ValueError("frames must be a 2D array or iterable, got a %d-channel signal" % sig.shape[1])
         fe = self._front_end(dev.index, dtype)
         packed = Packed(sig, [sig.shape[0]], fe.hop_size)
-        out = fe.run_packed(packed)
+        # Signal(norm=True) on a device tensor: fused as a per-clip gain, exactly as engine.run_chain does
+        norm = bool(getattr(data, "norm", False)) and not isinstance(data, np.ndarray)
+        scale = fe.peak_scales(packed, eps=0.0) if norm else None
+        out = fe.run_packed(packed, clip_scale=scale)
         return out.cpu().numpy()
 
 

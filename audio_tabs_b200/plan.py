@@ -314,15 +314,21 @@ class FrontEnd:
     # ---- device-resident hot path ----------------------------------------------------------
     def run_packed(self, packed: Packed, out: Optional[torch.Tensor] = None, flux: Optional[List] = None,
                    proj: Optional[List] = None, timing: Optional[List] = None,
-                   clip_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+                   clip_scale: Optional[torch.Tensor] = None,
+                   clip_status: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Launch the fused kernels for every resolution; returns the stacked (rows, width) tensor.
 
         ``out=False`` skips the stacked matrix (only ``flux`` / ``proj`` are written).
         ``clip_scale``: (n_clips,) float32 device tensor of per-clip gains applied before the logarithm
         (see :meth:`peak_scales`); ``timing``: a list that receives ``(resolution, start_event, end_event)`` per launch, recorded on
-        the stream the kernel runs on (read them after a synchronise).
+        the stream the kernel runs on (read them after a synchronise); ``clip_status``: (n_clips,) int32 device
+        tensor, zeroed by the caller, that receives per-clip status bits (``_ffi.CLIP_NONFINITE``: NaN / Inf
+        reached the clip's rows -- the other clips of the batch are unaffected).
         No synchronisation: results are ordered on the current stream.
         """
+        if clip_status is not None and (clip_status.dtype != torch.int32 or clip_status.numel() < packed.n_clips
+                                        or not clip_status.is_contiguous()):
+            raise ValueError("clip_status must be a contiguous int32 tensor with n_clips elements")
         if out is None:
             out = self.alloc_output(packed.total_frames)
         if out is not False and (out.shape != (packed.total_frames, self.width) or out.dtype != torch.float32
@@ -353,6 +359,7 @@ class FrontEnd:
             od.d_proj = proj[r].data_ptr() if proj is not None and proj[r] is not None else None
             od.ld_proj = proj[r].shape[1] if proj is not None and proj[r] is not None else 0
             od.d_clip_scale = clip_scale.data_ptr() if clip_scale is not None else None
+            od.d_clip_status = clip_status.data_ptr() if clip_status is not None else None
             ws = self._workspace(r, packed.n_clips)
             if timing is not None:
                 t0 = torch.cuda.Event(enable_timing=True)
@@ -501,18 +508,26 @@ class FrontEnd:
 
     # ---- host in / host out ----------------------------------------------------------------
     def process_batch(self, signals: Sequence, return_tensors: bool = False, peak_normalize: bool = False,
-                      eps: float = 1e-9):
+                      eps: float = 1e-9, return_status: bool = False):
         """signals: list of host arrays (float32 / int16; (N,) or (N, 2)). Returns one (T_i, width) per clip.
 
         ``peak_normalize``: each clip is treated as ``y / (max|y| + eps)`` -- what the reference does before
-        this path (/root/reference/backend/app/services/audio.py:24-26) -- fused as a per-clip gain."""
+        this path (/root/reference/backend/app/services/audio.py:24-26) -- fused as a per-clip gain.
+        ``return_status``: also return a (n_clips,) int32 numpy array of per-clip status bits (0 = fine,
+        ``_ffi.CLIP_NONFINITE`` = the clip's rows contain NaN / Inf because its samples did): one bad clip does
+        not poison the batch -- the reference's analogue is one failed Celery task
+        (/root/reference/backend/app/workers/tasks.py:35-38)."""
         packed = self.pack(signals)
         scale = self.peak_scales(packed, eps=eps) if peak_normalize else None
-        out = self.run_packed(packed, clip_scale=scale)
+        status = torch.zeros(max(packed.n_clips, 1), dtype=torch.int32, device=self.device) if return_status else None
+        out = self.run_packed(packed, clip_scale=scale, clip_status=status)
         if return_tensors:
-            return [out[packed.frame_off_host[i]:packed.frame_off_host[i + 1]] for i in range(packed.n_clips)]
+            res = [out[packed.frame_off_host[i]:packed.frame_off_host[i + 1]] for i in range(packed.n_clips)]
+            return (res, status[:packed.n_clips]) if return_status else res
         host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
         host.copy_(out, non_blocking=True)
+        st = status[:packed.n_clips].cpu().numpy() if return_status else None     # synchronises the stream
         torch.cuda.current_stream(self.device).synchronize()
         arr = host.numpy()
-        return [arr[packed.frame_off_host[i]:packed.frame_off_host[i + 1]] for i in range(packed.n_clips)]
+        res = [arr[packed.frame_off_host[i]:packed.frame_off_host[i + 1]] for i in range(packed.n_clips)]
+        return (res, st) if return_status else res

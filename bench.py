@@ -266,6 +266,149 @@ def pcie_bandwidth(dev, in_bytes, out_bytes):
             "both_directions_ms": ms_both}
 
 
+def fabric_concurrent(dev, in_bytes, out_bytes, barrier, world, reps=3):
+    """The host <-> device copy ceiling of THIS box for THIS step, measured with every rank copying at once:
+    after a barrier each rank starts one pinned H2D copy of its step's input and one D2H copy of its output
+    on two streams; the time is the max over ranks, best of `reps`.  At N > 1 the ranks share the host's
+    PCIe root / memory fabric, so this -- not rank 0's solo bandwidth times N -- is what e2e can reach."""
+    import torch
+    import torch.distributed as dist
+    hi = torch.empty(in_bytes, dtype=torch.uint8, pin_memory=True)
+    ho = torch.empty(out_bytes, dtype=torch.uint8, pin_memory=True)
+    di = torch.empty(in_bytes, dtype=torch.uint8, device=dev)
+    do = torch.empty(out_bytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    best = None
+    for _ in range(reps + 1):                      # first round is a warm-up
+        barrier()
+        cur = torch.cuda.current_stream(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(cur)
+        s1.wait_event(a)
+        s2.wait_event(a)
+        with torch.cuda.stream(s1):
+            di.copy_(hi, non_blocking=True)
+            e1 = torch.cuda.Event()
+            e1.record(s1)
+        with torch.cuda.stream(s2):
+            ho.copy_(do, non_blocking=True)
+            e2 = torch.cuda.Event()
+            e2.record(s2)
+        cur.wait_event(e1)
+        cur.wait_event(e2)
+        b.record(cur)
+        torch.cuda.synchronize(dev)
+        ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        best = ms if best is None or _ == 0 else min(best, ms)
+    del hi, ho, di, do
+    return best
+
+
+def time_e2e(fe, host_in, lens, host_out, steps, barrier, dev, world):
+    """`steps` passes of FrontEnd.process_batch_pinned (pinned host in -> device -> pinned host out), copies inside
+    the timed region; CUDA events on the current stream, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    for _ in range(2):
+        fe.process_batch_pinned(host_in, lens, host_out)
+    barrier()
+    t0 = time.perf_counter()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        fe.process_batch_pinned(host_in, lens, host_out)
+    b.record()
+    barrier()
+    ms = a.elapsed_time(b)
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms / steps, wall_ms / steps
+
+
+def timeit_events(fn, dev, warm=3, reps=5):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize(dev)
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize(dev)
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts))
+
+
+def other_configs(dev, peak, n_clips=256, seconds=180):
+    """The other BASELINE.json configs and SURVEY section 8(f) rows, device resident, measured in the same run
+    after the timed region (3 warm-ups, median of 5, CUDA events; inputs of 2-8 GB per step exceed L2):
+    ms, audio-s/s, algorithmic GB/s and its fraction of the measured HBM peak, FP32 TFLOP/s (algorithmic
+    flops, SURVEY section 8d formula) and its fraction of the 74.5 TFLOP/s CUDA-core peak."""
+    import torch
+    from audio_tabs_b200.frontends import log_filt_spec
+    from audio_tabs_b200.onsets import OnsetStrength
+    from audio_tabs_b200.plan import FrontEnd, Packed
+    from audio_tabs_b200.synth import synth_batch_device
+    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+    res = {}
+
+    def flops_per_frame(spec):
+        F = spec.frame_size
+        return 2.5 * F * np.log2(F) + F + 4 * F / 2 + 2 * len(spec.filterbank.banded()[3]) + 3 * spec.num_bands
+
+    def run(name, spec, nc, secs, dtype="f32", proj=False, what=""):
+        n = int(secs * SR)
+        sig = synth_batch_device(nc, n, seed=7, device=dev, dtype=dtype)
+        fe = FrontEnd([spec], device=dev.index, dtype=dtype)
+        packed = Packed(sig, [n] * nc, spec.hop_size)
+        if proj:
+            out = torch.empty((packed.total_frames, 12), dtype=torch.float32, device=dev)
+            fn = lambda: fe.run_packed(packed, out=False, proj=[out])  # noqa: E731
+        else:
+            out = fe.alloc_output(packed.total_frames)
+            fn = lambda: fe.run_packed(packed, out)  # noqa: E731
+        ms = timeit_events(fn, dev)
+        alg = sig.numel() * sig.element_size() + out.numel() * 4
+        tf = packed.total_frames * flops_per_frame(spec) / ms / 1e9
+        res[name] = {"what": what, "clips": nc, "seconds": secs, "frames": packed.total_frames, "ms": ms,
+                     "audio_s_per_s": nc * secs / ms * 1e3, "alg_gb": alg / 1e9, "alg_gbs": alg / ms / 1e6,
+                     "hbm_frac": alg / ms / 1e6 / peak, "fp32_tflops": tf, "fp32_frac": tf / fp32_peak}
+        del sig, out, packed, fe
+        torch.cuda.empty_cache()
+
+    run("1", log_filt_spec(2048, 441.0, 12), 1, 30, what="configs[0]: 1 x 30 s, frame 2048 / hop 441 / 12 bpo -> (3000, 81) (latency bound)")
+    run("3a", log_filt_spec(4096, 441.0, 24, 65.0, 2100.0, fold=True), n_clips, seconds, proj=True,
+        what="configs[2] at hop 441: frame 4096 -> 24 bpo 65-2100 Hz log filterbank (87 bands) -> 12-bin chroma")
+    run("3b", log_filt_spec(4096, 4410.0, 24, 65.0, 2100.0, fold=True), n_clips, seconds, proj=True,
+        what="configs[2] at hop 4410 (the app's chord rate, chords/extract.py:19)")
+    run("N1", log_filt_spec(8192, 4410.0, 24, 65.0, 2100.0), n_clips, seconds,
+        what="DeepChroma front end: frame 8192 @ fps 10 -> (1800, 105) (chords/extract.py:54)")
+    run("key", log_filt_spec(8192, 8820.0, 24, 65.0, 2100.0, int16=True), n_clips, seconds, dtype="i16",
+        what="CNN key front end: int16, frame 8192 @ fps 5 -> (900, 105) (theory/key.py:101)")
+    # N3: librosa-style onset strength (strum.py:114): frame 2048 hop 512, 128 mel, dB, median envelope
+    n = int(seconds * SR)
+    sig = synth_batch_device(n_clips, n, seed=9, device=dev)
+    eng = OnsetStrength(sr=SR, aggregate=np.median, device=dev.index)
+    packed = Packed(sig, [n] * n_clips, 512.0, "extend")
+    ms = timeit_events(lambda: eng.envelope(packed), dev)
+    alg = sig.numel() * 4 + packed.total_frames * 4
+    res["N3"] = {"what": "librosa onset_strength (2048 / 512, 128 mel, power_to_db, median)", "clips": n_clips, "seconds": seconds,
+                 "frames": packed.total_frames, "ms": ms, "audio_s_per_s": n_clips * seconds / ms * 1e3, "alg_gb": alg / 1e9,
+                 "alg_gbs": alg / ms / 1e6, "hbm_frac": alg / ms / 1e6 / peak}
+    del sig, packed, eng
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -286,7 +429,7 @@ def run_ours(args, rank, world, local_rank):
     n_clips = args.clips
     n_samples = int(args.clip_seconds * SR)
     specs = beat_specs()
-    fe = FrontEnd(specs, device=local_rank, dtype="f32", channels=1)
+    fe = FrontEnd(specs, device=local_rank, dtype="f32", channels=1, concurrent_streams=args.concurrent_streams)
     sig = synth_batch_device(n_clips, n_samples, seed=2000 + rank, device=dev)
     packed = Packed(sig, [n_samples] * n_clips, fe.hop_size)
     out = fe.alloc_output(packed.total_frames)
@@ -361,41 +504,48 @@ def run_ours(args, rank, world, local_rank):
                 "step_alg_gbs": (in_bytes + out_bytes) / ms_per_step / 1e6}
 
     # ---- end to end: pinned host in -> device -> pinned host out, copies inside the timed region
-    e2e = None
+    e2e = e2e_i16 = None
     if not args.no_e2e:
         host_in = torch.empty(sig.shape, dtype=sig.dtype, pin_memory=True)
         host_in.copy_(sig)
         host_out = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
         lens = [n_samples] * n_clips
-        for _ in range(2):
-            fe.process_batch_pinned(host_in, lens, host_out)
-        barrier()
-        t0 = time.perf_counter()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(args.steps):
-            fe.process_batch_pinned(host_in, lens, host_out)
-        b.record()
-        barrier()
-        e2e_ms = a.elapsed_time(b)
-        wall_ms = (time.perf_counter() - t0) * 1e3
-        if world > 1:
-            t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_ms = float(t.item())
-        e2e = {"value": world * audio_seconds / (e2e_ms / args.steps * 1e-3), "unit": UNIT,
+        e2e_ms, wall_ms = time_e2e(fe, host_in, lens, host_out, args.steps, barrier, dev, world)
+        e2e = {"value": world * audio_seconds / (e2e_ms * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": int(out_bytes),
-               "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps,
+               "ms_per_step": e2e_ms, "wall_ms_per_step": wall_ms,
                "api": "audio_tabs_b200.plan.FrontEnd.process_batch_pinned", "numa_bound_cpus": len(numa_cpus)}
+        # the copy ceiling with EVERY rank copying at once (one H2D + one D2H of the step's bytes per rank)
+        fab_ms = fabric_concurrent(dev, int(in_bytes), int(out_bytes), barrier, world)
+        e2e["fabric_concurrent_ms"] = fab_ms
+        e2e["fabric_concurrent_value"] = world * audio_seconds / (fab_ms * 1e-3)
+        e2e["frac_of_fabric_concurrent"] = e2e["value"] / e2e["fabric_concurrent_value"]
+        e2e["fabric_gbs_per_gpu"] = {"h2d": in_bytes / fab_ms / 1e6, "d2h": out_bytes / fab_ms / 1e6}
+        # int16 PCM ingest (the reference's audio is PCM-16 on disk: services/audio.py:18-21, pipeline.py:1672,
+        # theory/key.py:144): same clips quantised to int16, window / 32767 as madmom does -- half the H2D bytes
+        if not args.no_i16:
+            fe16 = FrontEnd(beat_specs(int16=True), device=local_rank, dtype="i16", channels=1)
+            host_in16 = torch.empty(sig.shape, dtype=torch.int16, pin_memory=True)
+            host_in16.copy_((sig * 32767.0).round().clamp_(-32768, 32767).to(torch.int16))
+            ms16, wall16 = time_e2e(fe16, host_in16, lens, host_out, args.steps, barrier, dev, world)
+            fab16 = fabric_concurrent(dev, int(in_bytes // 2), int(out_bytes), barrier, world)
+            e2e_i16 = {"value": world * audio_seconds / (ms16 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(in_bytes // 2),
+                       "d2h_bytes_per_step": int(out_bytes), "ms_per_step": ms16, "wall_ms_per_step": wall16,
+                       "fabric_concurrent_ms": fab16, "fabric_concurrent_value": world * audio_seconds / (fab16 * 1e-3),
+                       "note": "same workload with int16 PCM input (madmom semantics: window / 32767); not the headline"}
+            e2e_i16["frac_of_fabric_concurrent"] = e2e_i16["value"] / e2e_i16["fabric_concurrent_value"]
+            del host_in16, fe16
         del host_in, host_out
         if rank == 0:
             pc = pcie_bandwidth(dev, int(in_bytes), int(out_bytes))
-            e2e["pcie"] = pc
-            # strict bound: the step cannot be faster than its larger one-direction copy running alone;
-            # reference point: ONE copy of each direction started together (best of three) -- the pipeline's
-            # chunked copies interleave at least as well, so e2e can land slightly above it
-            e2e["pcie_bound_value"] = world * audio_seconds / (max(pc["h2d_ms"], pc["d2h_ms"]) * 1e-3)
-            e2e["pcie_concurrent_value"] = world * audio_seconds / (pc["both_directions_ms"] * 1e-3)
+            e2e["pcie_solo_rank0"] = pc          # rank 0 alone (no other rank copying): NOT the N-GPU ceiling
+            e2e["pcie_bound_value_per_gpu"] = audio_seconds / (max(pc["h2d_ms"], pc["d2h_ms"]) * 1e-3)
+
+    configs = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        del sig, out, packed
+        torch.cuda.empty_cache()
+        configs = other_configs(dev, peak)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -409,9 +559,141 @@ def run_ours(args, rank, world, local_rank):
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": bench_config(n_clips, args.clip_seconds, world),
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_i16": e2e_i16, "configs": configs,
+            "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _dist_setup(world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from audio_tabs_b200.sharding import bind_to_gpu_numa
+    numa = bind_to_gpu_numa(local_rank)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+    return dev, barrier, max_over_ranks, numa
+
+
+def run_config4(args, rank, world, local_rank):
+    """BASELINE configs[3]: 4096 synthetic 3-min clips job-sharded over 2 / 4 / 8 GPUs, full beat front end,
+    inputs generated on the device, no inter-GPU traffic.  Every rank holds 4096 / N clips resident (512 at
+    N = 8: 16.3 GB in + 11.6 GB out, 1024 at N = 4); with fewer GPUs a slice runs (1024 clips per GPU at N = 2,
+    512 on one GPU -- its 4096 clips would need 222 GB) and the line says so: audio-s/s does not depend on the
+    clip count on this path."""
+    import torch
+    import torch.distributed as dist
+    from audio_tabs_b200 import _ffi
+    from audio_tabs_b200.frontends import beat_specs
+    from audio_tabs_b200.plan import FrontEnd, Packed
+    from audio_tabs_b200.synth import synth_batch_device
+    dev, barrier, max_over_ranks, _ = _dist_setup(world, local_rank)
+    total_clips = 4096
+    per_gpu = min(total_clips // world, 1024) if world >= 2 else 512      # <= 32.5 GB in + 23.2 GB out resident per GPU
+    n = CLIP_SECONDS * SR
+    specs = beat_specs()
+    fe = FrontEnd(specs, device=local_rank)
+    sig = synth_batch_device(per_gpu, n, seed=4000 + rank, device=dev)
+    packed = Packed(sig, [n] * per_gpu, fe.hop_size)
+    out = fe.alloc_output(packed.total_frames)
+    for _ in range(args.warmup):
+        fe.run_packed(packed, out)
+    barrier()
+    n0 = _ffi.launch_count()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        fe.run_packed(packed, out)
+    b.record()
+    barrier()
+    ms = max_over_ranks(a.elapsed_time(b)) / args.steps
+    launches = _ffi.launch_count() - n0
+    peak, peak_src = load_peaks()
+    alg = sig.numel() * 4 + out.numel() * 4
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": world * per_gpu * CLIP_SECONDS / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[3]: 4096 x 180 s clips job-sharded, full beat front end -> (18000,314)/clip",
+                       "clips_per_gpu": per_gpu, "clips_total_this_run": per_gpu * world,
+                       "slice": None if per_gpu * world == total_clips else
+                       "%d of 4096 clips (%d per GPU resident: 16.3 GB in + 11.6 GB out); throughput is clip-count invariant" % (per_gpu * world, per_gpu),
+                       "parallelism": "job-sharded x%d, no collective on the data path" % world,
+                       "l2": "27.9 GB per GPU per step exceed the 126 MB L2"},
+            "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": alg / ms / 1e6 / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "whole step (three k_front_pair launches), per GPU"},
+            "peak_device_memory_gb": torch.cuda.max_memory_allocated(dev) / 1e9, "gpu_launches": int(launches)}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_config5(args, rank, world, local_rank):
+    """BASELINE configs[4]: long-form 10-min STEREO f32 Demucs-shaped stems, 4 stems per job, 512 jobs on 8 GPUs
+    (64 jobs = 54 GB of input per GPU): streamed through FrontEnd.process_batch_pinned (two device slots, three
+    streams, stereo down-mix fused into the kernels' loads), never resident at once.  Host memory is bounded
+    too: one pinned block of 16 stems is streamed repeatedly (the audio is synthetic anyway) -- a PIPELINE and
+    memory-sizing stress, not 433 GB of distinct host data."""
+    import torch
+    import torch.distributed as dist
+    from audio_tabs_b200.frontends import beat_specs
+    from audio_tabs_b200.plan import FrontEnd
+    dev, barrier, max_over_ranks, _ = _dist_setup(world, local_rank)
+    seconds, jobs_per_gpu, stems_per_pass = 600, args.jobs_per_gpu, 16
+    n = seconds * SR
+    passes = max(1, jobs_per_gpu * 4 // stems_per_pass)
+    fe = FrontEnd(beat_specs(), device=local_rank, dtype="f32", channels=2)
+    gen = torch.Generator(device=dev).manual_seed(5000 + rank)
+    host_in = torch.empty((stems_per_pass * n, 2), dtype=torch.float32, pin_memory=True)
+    for i in range(stems_per_pass):
+        host_in[i * n:(i + 1) * n].copy_(torch.randn((n, 2), generator=gen, device=dev) * 0.1)
+    lens = [n] * stems_per_pass
+    frames = -(-n // 441) * stems_per_pass
+    host_out = torch.empty((frames, fe.width), dtype=torch.float32, pin_memory=True)
+    torch.cuda.synchronize(dev)
+    torch.cuda.reset_peak_memory_stats(dev)
+    fe.process_batch_pinned(host_in, lens, host_out, group_clips=1)
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(passes):
+        fe.process_batch_pinned(host_in, lens, host_out, group_clips=1)
+    b.record()
+    barrier()
+    ms = max_over_ranks(a.elapsed_time(b))
+    stems = stems_per_pass * passes
+    if rank == 0:
+        print(json.dumps({
+            "metric": "stem-seconds/s, beat front end on streamed 10-min stereo stems (BASELINE configs[4])",
+            "value": world * stems * seconds / ms * 1e3, "unit": "audio-s/s", "n_gpus": world, "steps": passes, "warmup": 1,
+            "ms_per_step": ms / passes, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "BASELINE configs[4]: %d jobs/GPU x 4 stems x 600 s stereo f32, streamed pinned host -> device -> pinned host" % jobs_per_gpu,
+                       "stems_per_gpu": stems, "parallelism": "job-sharded x%d" % world,
+                       "host_data": "one pinned block of 16 stems (3.4 GB) re-streamed %d times per GPU" % passes},
+            "e2e": {"value": world * stems * seconds / ms * 1e3, "unit": "audio-s/s",
+                    "h2d_bytes_per_step": stems_per_pass * n * 8, "d2h_bytes_per_step": frames * fe.width * 4},
+            "h2d_gbs_per_gpu": stems * n * 8 / ms / 1e6, "total_ms": ms,
+            "peak_device_memory_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
+            "pinned_host_gb_per_gpu": (host_in.numel() + host_out.numel()) * 4 / 1e9}), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -427,6 +709,13 @@ def main():
     ap.add_argument("--clip-seconds", type=float, default=CLIP_SECONDS)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-i16", action="store_true", help="skip the int16 end-to-end arm")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configs (measured after the timed region)")
+    ap.add_argument("--concurrent-streams", action="store_true", help="launch the three resolutions on three streams")
+    ap.add_argument("--jobs-per-gpu", type=int, default=64, help="--config 5: jobs (of 4 stems) streamed per GPU")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 4, 5],
+                    help="2: BASELINE configs[1] (default, the contract line); 4: configs[3] 4096 clips job-sharded; "
+                         "5: configs[4] 10-min stereo stems streamed")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -439,6 +728,10 @@ def main():
         sys.exit(subprocess.call(cmd))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.config == 4:
+        run_config4(args, rank, world, local_rank)
+    elif args.config == 5:
+        run_config5(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)
 

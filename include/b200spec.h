@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define B200SPEC_ABI_VERSION 2
+#define B200SPEC_ABI_VERSION 3
 #define B200SPEC_MAX_RES 4          /* resolutions per plan (RNNBeatProcessor uses 3) */
 #define B200SPEC_MAX_DIFF_FRAMES 16 /* largest supported diff lag in frames */
 
@@ -124,12 +124,21 @@ typedef struct b200spec_out_desc {
   float *d_flux;     /* (total_frames,) row sums of the difference (spectral flux), or NULL */
   float *d_proj;     /* (total_frames, ld_proj) projection output, or NULL */
   int64_t ld_proj;
-  /* optional per-clip gain applied to the band sums before the logarithm (n_clips floats, device).
-   * The path is linear up to there, so scale[c] = 1 / (max|x_c| + 1e-9) from b200spec_clip_peak gives
-   * the spectrogram of the peak-normalised clip (services/audio.py:24-26 peak_normalize; madmom
-   * Signal(norm=True)) without a pass that rewrites the samples.  NULL = no gain. */
+  /* optional per-clip gain g_c on the SAMPLES of clip c, applied to the band sums before the logarithm
+   * (n_clips floats, device).  The magnitude path is linear, so the band sums of g_c * x are g_c times
+   * those of x -- and g_c^2 times for a power spectrogram (res_desc.power = 1), which the kernel accounts
+   * for.  scale[c] = 1 / (max|x_c| + 1e-9) from b200spec_clip_peak therefore gives the spectrogram of the
+   * peak-normalised clip (services/audio.py:24-26 peak_normalize; madmom Signal(norm=True)) without a
+   * pass that rewrites the samples.  NULL = no gain. */
   const float *d_clip_scale;
+  /* optional per-clip status word (n_clips int32, device; the caller zeroes it): bit 0 is OR-ed in when a
+   * non-finite value (NaN / Inf samples) reached clip c's output rows.  Clips are independent -- a bad
+   * clip never changes another clip's rows -- so a batch can be triaged per clip (SURVEY.md section 5:
+   * "a failed shard must not poison the batch").  NULL = not wanted. */
+  int32_t *d_clip_status;
 } b200spec_out_desc;
+
+#define B200SPEC_CLIP_NONFINITE 1
 
 int b200spec_abi_version(void);
 const char *b200spec_last_error(void);

@@ -517,3 +517,65 @@ def test_other_windows_use_the_table_path(b2, window):
         got = np.asarray(b2.SpectrogramDifferenceProcessor(diff_frames=1, positive_diffs=True, stack_diffs=np.hstack)(log))
         assert got.shape == want.shape
         assert_close(got, want, what="log spec + diff, frame %d" % frame_size)
+
+
+# ---- round 2: per-clip status, gain on power spectrograms, non-current device ---------------------------
+def test_clip_status_and_batch_isolation(b2):
+    """A clip with NaN / Inf samples sets ITS status bit and leaves the other clips' rows bitwise unchanged
+    ("a failed shard must not poison the batch")."""
+    import torch
+    from audio_tabs_b200 import _ffi
+    from audio_tabs_b200.frontends import beat_specs
+    from audio_tabs_b200.plan import FrontEnd
+    from audio_tabs_b200.synth import synth_guitar
+    clips = [synth_guitar(3500 + i, 1.0 + 0.3 * i) for i in range(4)]
+    bad = [c.copy() for c in clips]
+    bad[1][12345] = np.nan
+    bad[3][777] = np.inf
+    fe = FrontEnd(beat_specs(), device=0)
+    clean, st0 = fe.process_batch(clips, return_status=True)
+    got, st = fe.process_batch(bad, return_status=True)
+    assert st0.dtype == np.int32 and st0.tolist() == [0, 0, 0, 0]
+    assert st.tolist() == [0, _ffi.CLIP_NONFINITE, 0, _ffi.CLIP_NONFINITE]
+    for i in (0, 2):
+        assert np.array_equal(got[i], clean[i])
+    assert not np.isfinite(got[1]).all() and not np.isfinite(got[3]).all()
+    rows = np.nonzero(~np.isfinite(got[1]).all(axis=1))[0]            # only the frames that contain the sample
+    assert rows.min() >= (12345 - 2048) // 441 - 2 and rows.max() <= (12345 + 2048) // 441 + 3
+    # the single-frame kernel (frame 8192) reports it as well
+    from audio_tabs_b200.frontends import log_filt_spec
+    fe8 = FrontEnd([log_filt_spec(8192, 4410.0, 24, 65.0, 2100.0)], device=0)
+    _, st8 = fe8.process_batch(bad, return_status=True)
+    assert st8.tolist() == [0, 1, 0, 1]
+
+
+def test_peak_normalisation_of_a_power_spectrogram(b2):
+    """the per-clip gain on a power (|X|^2) filterbank is gain^2 -- dB mel spectrogram of the
+    peak-normalised clip == fused gain on the raw clip."""
+    import torch
+    from audio_tabs_b200.onsets import mel_db_spec
+    from audio_tabs_b200.plan import FrontEnd
+    from audio_tabs_b200.synth import synth_guitar
+    clips = [synth_guitar(3600 + i, 1.0) * s for i, s in enumerate((0.07, 0.9, 0.31))]
+    fe = FrontEnd([mel_db_spec(44100)], device=0, end="extend")
+    fused = fe.process_batch(clips, peak_normalize=True, eps=0.0)
+    plain = fe.process_batch([c / np.abs(c).max() for c in clips])
+    for a, b in zip(fused, plain):
+        # 10 log10: a wrong (linear) gain would be off by 10 log10(g) = up to 11.5 dB here
+        assert np.abs(a - b).max() < 2e-3, np.abs(a - b).max()
+
+
+def test_planless_calls_follow_the_pointer_device(b2):
+    """context_stack / onset_envelope / magnitude launch on the device that owns their input,
+    whatever the current device is (needs two GPUs)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from audio_tabs_b200.audio.chroma import context_stack_device
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal((50, 105)).astype(np.float32)
+    with torch.cuda.device(0):
+        t = torch.from_numpy(x).to("cuda:1")
+        got = context_stack_device(t, 15)
+        torch.cuda.synchronize(1)
+    assert got.device.index == 1 and np.array_equal(got.cpu().numpy(), ref.dcp_context(x, 15))
