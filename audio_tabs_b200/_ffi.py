@@ -9,7 +9,7 @@ import ctypes as C
 import os
 from pathlib import Path
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_RES = 4
 MAX_DIFF_FRAMES = 16
 
@@ -89,6 +89,9 @@ SYMBOLS = [
                                        C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     ("b200spec_logfilt", C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                    C.c_int64, C.POINTER(OutDesc), C.c_void_p, C.c_size_t, C.c_void_p]),
+    ("b200spec_logfilt_multi", C.c_int, [C.c_void_p, C.c_int32, c_int32_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                         C.c_int64, C.POINTER(OutDesc), C.c_void_p, C.c_size_t, C.c_void_p]),
+    ("b200spec_logfilt_multi_supported", C.c_int, [C.c_void_p, C.c_int32, c_int32_p]),
     ("b200spec_clip_peak", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_int32,
                                      C.c_void_p, C.c_void_p]),
     ("b200spec_context_stack", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int64,

@@ -22,7 +22,7 @@ LIBDIR = PKG / "lib"
 OBJDIR = PKG / "build"
 LIB = LIBDIR / "libb200spec.so"
 
-SOURCES = ["b200spec.cu", "front_f1024.cu", "front_f2048.cu", "front_f4096.cu", "front_f8192.cu"]
+SOURCES = ["b200spec.cu", "front_f1024.cu", "front_f2048.cu", "front_f4096.cu", "front_f8192.cu", "front_multi.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

@@ -198,11 +198,14 @@ int build_res(b200spec_plan *pl, const b200spec_res_desc &d, ResPlan &r) {
   if ((rc = upload(pl, pt.data(), pt.size(), &r.d_pt))) return rc;
   if (F <= 4096) {   // pair transform (two frames as one complex FFT of F points): N' = F, R3' = F / 256
     const int R3p = F / 256;
-    std::vector<float2> ptw3(129 * R3p), pwr(2 * R3p);
+    int rows = 0;
+    while ((1 << rows) < R3p) ++rows;
+    // compact table: row r = W_F^(2^r q) -- the only rows the last pass reads (tw3_rows forms the others as products)
+    std::vector<float2> ptw3(129 * rows), pwr(2 * R3p);
     for (int q = 0; q <= 128; ++q)
-      for (int n3 = 0; n3 < R3p; ++n3) {
-        double a = -2.0 * PI * (double)(n3 * q) / (double)F;
-        ptw3[n3 * 129 + q] = make_float2((float)cos(a), (float)sin(a));
+      for (int r3 = 0; r3 < rows; ++r3) {
+        double a = -2.0 * PI * (double)((1 << r3) * q) / (double)F;
+        ptw3[r3 * 129 + q] = make_float2((float)cos(a), (float)sin(a));
       }
     for (int e = 0; e < 2 * R3p; ++e) {
       double a = -2.0 * PI * (double)e / (double)(2 * R3p);
@@ -349,39 +352,9 @@ int choose_chunk(const b200spec_plan *pl, int F, long long total_frames, int kd)
   return (int)chunk;
 }
 
-int launch_front(const b200spec_plan *pl, int res, int mode, const void *d_sig, const int64_t *d_clip_off,
-                 const int64_t *d_frame_off, int n_clips, int64_t total_frames, b2::FrontParams &p,
-                 void *d_workspace, size_t workspace_bytes, void *stream) {
-  if (!pl) return fail(B200SPEC_ERR_ARG, "plan is NULL");
-  if (res < 0 || res >= pl->num_res) return fail(B200SPEC_ERR_ARG, "resolution %d out of range", res);
-  if (n_clips < 0 || total_frames < 0) return fail(B200SPEC_ERR_ARG, "negative sizes");
-  if (n_clips == 0 || total_frames == 0) return 0;
-  if (!d_sig || !d_clip_off || !d_frame_off) return fail(B200SPEC_ERR_ARG, "NULL device pointer");
-  const ResPlan &r = pl->res[res];
-  Workspace w;
-  int rc = carve_workspace(d_workspace, workspace_bytes, n_clips, w);
-  if (rc) return rc;
-  DeviceGuard guard;
-  CU_CHECK(guard.enter(pl->device));
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  static const char *const kRangeNames[2][4] = {
-      {"b200spec front end 1024", "b200spec front end 2048", "b200spec front end 4096", "b200spec front end 8192"},
-      {"b200spec stft 1024", "b200spec stft 2048", "b200spec stft 4096", "b200spec stft 8192"}};
-  NvtxRange range(kRangeNames[mode == b2::MODE_LOGFILT ? 0 : 1][r.frame_size == 1024 ? 0 : r.frame_size == 2048 ? 1 : r.frame_size == 4096 ? 2 : 3]);
-
-  const int chunk = choose_chunk(pl, r.frame_size, total_frames, mode == b2::MODE_LOGFILT ? r.diff_frames : 0);
-  b2::k_setup_tasks<<<1, 1024, 0, st>>>(reinterpret_cast<const long long *>(d_frame_off), n_clips, chunk,
-                                         w.task_off, w.counter);
-  CU_CHECK(cudaGetLastError());
-  g_launches++;
-
-  p.sig = d_sig;
-  p.clip_off = reinterpret_cast<const long long *>(d_clip_off);
-  p.frame_off = reinterpret_cast<const long long *>(d_frame_off);
-  p.n_clips = n_clips;
-  p.task_off = w.task_off;
-  p.task_counter = w.counter;
-  p.chunk = chunk;
+// everything of FrontParams that comes from the plan (tables, filterbank, constants)
+void fill_plan_params(const b200spec_plan *pl, const ResPlan &r, b2::FrontParams &p) {
+  p.frame_size = r.frame_size;
   p.hop = r.hop;
   p.origin = r.origin;
   p.window = r.d_window;
@@ -416,13 +389,54 @@ int launch_front(const b200spec_plan *pl, int res, int mode, const void *d_sig, 
   p.proj_off = r.d_proj_off;
   p.proj_band = r.d_proj_band;
   p.proj_w = r.d_proj_w;
+  (void)pl;
+}
+
+const char *range_name(int mode, int frame_size) {
+  static const char *const kRangeNames[2][4] = {
+      {"b200spec front end 1024", "b200spec front end 2048", "b200spec front end 4096", "b200spec front end 8192"},
+      {"b200spec stft 1024", "b200spec stft 2048", "b200spec stft 4096", "b200spec stft 8192"}};
+  return kRangeNames[mode == b2::MODE_LOGFILT ? 0 : 1][frame_size == 1024 ? 0 : frame_size == 2048 ? 1 : frame_size == 4096 ? 2 : 3];
+}
+
+int launch_front(const b200spec_plan *pl, int res, int mode, const void *d_sig, const int64_t *d_clip_off,
+                 const int64_t *d_frame_off, int n_clips, int64_t total_frames, b2::FrontParams &p,
+                 void *d_workspace, size_t workspace_bytes, void *stream) {
+  if (!pl) return fail(B200SPEC_ERR_ARG, "plan is NULL");
+  if (res < 0 || res >= pl->num_res) return fail(B200SPEC_ERR_ARG, "resolution %d out of range", res);
+  if (n_clips < 0 || total_frames < 0) return fail(B200SPEC_ERR_ARG, "negative sizes");
+  if (n_clips == 0 || total_frames == 0) return 0;
+  if (!d_sig || !d_clip_off || !d_frame_off) return fail(B200SPEC_ERR_ARG, "NULL device pointer");
+  const ResPlan &r = pl->res[res];
+  Workspace w;
+  int rc = carve_workspace(d_workspace, workspace_bytes, n_clips, w);
+  if (rc) return rc;
+  DeviceGuard guard;
+  CU_CHECK(guard.enter(pl->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  NvtxRange range(range_name(mode, r.frame_size));
+
+  const int chunk = choose_chunk(pl, r.frame_size, total_frames, mode == b2::MODE_LOGFILT ? r.diff_frames : 0);
+  b2::k_setup_tasks<<<1, 1024, 0, st>>>(reinterpret_cast<const long long *>(d_frame_off), n_clips, chunk,
+                                         w.task_off, w.counter);
+  CU_CHECK(cudaGetLastError());
+  g_launches++;
+
+  p.sig = d_sig;
+  p.clip_off = reinterpret_cast<const long long *>(d_clip_off);
+  p.frame_off = reinterpret_cast<const long long *>(d_frame_off);
+  p.n_clips = n_clips;
+  p.task_off = w.task_off;
+  p.task_counter = w.counter;
+  p.chunk = chunk;
+  fill_plan_params(pl, r, p);
 
   const int in = (pl->dtype == B200SPEC_I16 ? 2 : 0) + (pl->channels == 2 ? 1 : 0);
   const long long task_bound = total_frames / chunk + n_clips;
   cudaError_t e;
-  // The log-filtered path of frames <= 4096 runs the pair kernel (two frames per complex FFT);
-  // B200SPEC_PAIR=0 keeps the one-frame kernel (A/B measurements), as does a configuration whose
-  // tables do not fit next to the larger FFT buffer.
+  // The log-filtered path of frames <= 4096 runs the pair kernel (two frames per complex FFT); a configuration
+  // whose tables do not fit next to the larger FFT buffer keeps the one-frame kernel (as does B200SPEC_PAIR=0 in a
+  // tuning build: A/B measurements).
 #ifdef B200SPEC_TUNING
   static const bool use_pair = []() { const char *v = getenv("B200SPEC_PAIR"); return !(v && v[0] == '0'); }();
 #else
@@ -456,6 +470,31 @@ int launch_front(const b200spec_plan *pl, int res, int mode, const void *d_sig, 
                 "shared memory than an SM has; use the unfused stft / filter_log calls", r.frame_size, r.num_bands);
   if (e != cudaSuccess) return fail(B200SPEC_ERR_CUDA, "front-end kernel launch failed: %s", cudaGetErrorString(e));
   g_launches++;
+  return 0;
+}
+
+void fill_out_params(const b200spec_out_desc &out, const ResPlan &r, b2::FrontParams &p) {
+  p.out = out.d_out;
+  p.ld_out = out.ld_out;
+  p.col_spec = out.col_spec;
+  p.col_diff = out.col_diff;
+  p.flux = out.d_flux;
+  p.clip_scale = out.d_clip_scale;
+  p.clip_status = out.d_clip_status;
+  p.proj = out.d_proj;
+  p.ld_proj = out.ld_proj;
+  p.num_classes = out.d_proj ? r.num_classes : 0;
+  p.nproj = out.d_proj ? r.nproj : 0;
+}
+
+int check_out_desc(const b200spec_out_desc &out, const ResPlan &r, int res) {
+  if (r.num_bands <= 0) return fail(B200SPEC_ERR_ARG, "resolution %d has no filterbank; use b200spec_spectrogram", res);
+  if (out.d_proj && r.num_classes <= 0) return fail(B200SPEC_ERR_ARG, "d_proj given but the plan has no projection");
+  if (out.d_out && out.ld_out < r.num_bands) return fail(B200SPEC_ERR_ARG, "ld_out smaller than num_bands");
+  if (out.col_diff >= 0 && r.diff_frames <= 0) return fail(B200SPEC_ERR_ARG, "col_diff given but diff_frames == 0");
+  if (r.diff_max_bins > 1 && (out.col_diff >= 0 || out.d_flux))
+    return fail(B200SPEC_ERR_UNSUPPORTED, "diff_max_bins > 1: the fused kernel writes the log-filtered rows only; "
+                "compute the SuperFlux difference with b200spec_diff_flux_chroma on them");
   return 0;
 }
 
@@ -562,27 +601,93 @@ int b200spec_logfilt(const b200spec_plan *plan, int32_t res, const void *d_sig, 
   if (!out) return fail(B200SPEC_ERR_ARG, "out descriptor is NULL");
   if (res < 0 || res >= plan->num_res) return fail(B200SPEC_ERR_ARG, "resolution %d out of range", res);
   const ResPlan &r = plan->res[res];
-  if (r.num_bands <= 0) return fail(B200SPEC_ERR_ARG, "resolution %d has no filterbank; use b200spec_spectrogram", res);
-  if (out->d_proj && r.num_classes <= 0) return fail(B200SPEC_ERR_ARG, "d_proj given but the plan has no projection");
-  if (out->d_out && out->ld_out < r.num_bands) return fail(B200SPEC_ERR_ARG, "ld_out smaller than num_bands");
-  if (out->col_diff >= 0 && r.diff_frames <= 0) return fail(B200SPEC_ERR_ARG, "col_diff given but diff_frames == 0");
-  if (r.diff_max_bins > 1 && (out->col_diff >= 0 || out->d_flux))
-    return fail(B200SPEC_ERR_UNSUPPORTED, "diff_max_bins > 1: the fused kernel writes the log-filtered rows only; "
-                "compute the SuperFlux difference with b200spec_diff_flux_chroma on them");
+  if (int rc = check_out_desc(*out, r, res)) return rc;
   b2::FrontParams p{};
-  p.out = out->d_out;
-  p.ld_out = out->ld_out;
-  p.col_spec = out->col_spec;
-  p.col_diff = out->col_diff;
-  p.flux = out->d_flux;
-  p.clip_scale = out->d_clip_scale;
-  p.clip_status = out->d_clip_status;
-  p.proj = out->d_proj;
-  p.ld_proj = out->ld_proj;
-  p.num_classes = out->d_proj ? r.num_classes : 0;
-  p.nproj = out->d_proj ? r.nproj : 0;
+  fill_out_params(*out, r, p);
   return launch_front(plan, res, b2::MODE_LOGFILT, d_sig, d_clip_off, d_frame_off, n_clips, total_frames, p,
                       d_workspace, workspace_bytes, stream);
+}
+
+int b200spec_logfilt_multi_supported(const b200spec_plan *plan, int32_t n_res, const int32_t *res) {
+  if (!plan || !res || n_res < 1 || n_res > b2::kMultiMaxRes) return 0;
+  b2::MultiParams m{};
+  m.n_res = n_res;
+  for (int i = 0; i < n_res; ++i) {
+    if (res[i] < 0 || res[i] >= plan->num_res) return 0;
+    const ResPlan &r = plan->res[res[i]];
+    if (r.frame_size > 4096 || r.num_bands <= 0 || r.d_pair_tw3 == nullptr || r.fb_w4_global) return 0;
+    if (r.hop != plan->res[res[0]].hop || r.origin != plan->res[res[0]].origin) return 0;
+    fill_plan_params(plan, r, m.r[i]);
+    m.r[i].num_classes = r.num_classes;     // worst case for the shared-memory plan: projection tables staged
+    m.r[i].nproj = r.nproj;
+  }
+  return b2::multi_smem_layout(m, b2::kMultiGroups) <= b2::kMaxSmemPerCta ? 1 : 0;
+}
+
+int b200spec_logfilt_multi(const b200spec_plan *plan, int32_t n_res, const int32_t *res, const void *d_sig,
+                           const int64_t *d_clip_off, const int64_t *d_frame_off, int32_t n_clips,
+                           int64_t total_frames, const b200spec_out_desc *outs, void *d_workspace,
+                           size_t workspace_bytes, void *stream) {
+  if (!plan) return fail(B200SPEC_ERR_ARG, "plan is NULL");
+  if (!res || !outs) return fail(B200SPEC_ERR_ARG, "res / outs is NULL");
+  if (n_res < 1 || n_res > b2::kMultiMaxRes) return fail(B200SPEC_ERR_ARG, "n_res %d outside [1, %d]", n_res, b2::kMultiMaxRes);
+  if (n_clips < 0 || total_frames < 0) return fail(B200SPEC_ERR_ARG, "negative sizes");
+  b2::MultiParams m{};
+  m.n_res = n_res;
+  int kd_max = 0;
+  for (int i = 0; i < n_res; ++i) {
+    if (res[i] < 0 || res[i] >= plan->num_res) return fail(B200SPEC_ERR_ARG, "resolution %d out of range", res[i]);
+    const ResPlan &r = plan->res[res[i]];
+    if (int rc = check_out_desc(outs[i], r, res[i])) return rc;
+    if (r.frame_size > 4096 || r.d_pair_tw3 == nullptr)
+      return fail(B200SPEC_ERR_UNSUPPORTED, "the one-launch kernel runs frame sizes 1024 / 2048 / 4096 (got %d)", r.frame_size);
+    if (r.fb_w4_global) return fail(B200SPEC_ERR_UNSUPPORTED, "resolution %d: filterbank table too large for the one-launch kernel", res[i]);
+    if (r.hop != plan->res[res[0]].hop || r.origin != plan->res[res[0]].origin)
+      return fail(B200SPEC_ERR_ARG, "all resolutions of one launch must share hop_size and origin (rows are per frame)");
+    if (r.diff_frames > kd_max) kd_max = r.diff_frames;
+  }
+  if (n_clips == 0 || total_frames == 0) return 0;
+  if (!d_sig || !d_clip_off || !d_frame_off) return fail(B200SPEC_ERR_ARG, "NULL device pointer");
+  Workspace w;
+  if (int rc = carve_workspace(d_workspace, workspace_bytes, n_clips, w)) return rc;
+  DeviceGuard guard;
+  CU_CHECK(guard.enter(plan->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  NvtxRange range("b200spec front end (all resolutions, one launch)");
+
+  // one task list for all resolutions: (clip, chunk of frames); every resolution of a task runs on the same group
+  const long long slots = (long long)plan->num_sms * b2::kMultiGroups;
+  long long chunk = total_frames / (slots * 8);
+  if (chunk < 16) chunk = 16;
+  if (chunk > 96) chunk = 96;
+  if (chunk >= 16) chunk -= (chunk + kd_max) % 4;
+  b2::k_setup_tasks<<<1, 1024, 0, st>>>(reinterpret_cast<const long long *>(d_frame_off), n_clips, (int)chunk,
+                                         w.task_off, w.counter);
+  CU_CHECK(cudaGetLastError());
+  g_launches++;
+  for (int i = 0; i < n_res; ++i) {
+    const ResPlan &r = plan->res[res[i]];
+    b2::FrontParams &p = m.r[i];
+    fill_out_params(outs[i], r, p);
+    p.sig = d_sig;
+    p.clip_off = reinterpret_cast<const long long *>(d_clip_off);
+    p.frame_off = reinterpret_cast<const long long *>(d_frame_off);
+    p.n_clips = n_clips;
+    p.task_off = w.task_off;
+    p.task_counter = w.counter;
+    p.chunk = (int)chunk;
+    fill_plan_params(plan, r, p);
+    p.tw3 = r.d_pair_tw3;
+    p.wr = r.d_pair_wr;
+  }
+  const int in = (plan->dtype == B200SPEC_I16 ? 2 : 0) + (plan->channels == 2 ? 1 : 0);
+  const long long task_bound = total_frames / chunk + n_clips;
+  const cudaError_t e = b2_launch_multi(in, m, plan->num_sms, task_bound, st);
+  if (e == cudaErrorInvalidConfiguration)
+    return fail(B200SPEC_ERR_UNSUPPORTED, "these resolutions do not fit one launch (shared memory); use b200spec_logfilt per resolution");
+  if (e != cudaSuccess) return fail(B200SPEC_ERR_CUDA, "front-end (one-launch) kernel launch failed: %s", cudaGetErrorString(e));
+  g_launches++;
+  return 0;
 }
 
 int b200spec_clip_peak(const b200spec_plan *plan, const void *d_sig, const int64_t *d_clip_off, int32_t n_clips,

@@ -35,17 +35,18 @@ struct MagLinear {
     for (int t = 0; t < TBF; ++t) m[t] = mags[t * MS + k];
   }
 };
-// MagInterleaved: the TB frames of a tail batch are interleaved per bin (bin k of frame t at k * TB + t), so
+// MagInterleaved: the TBF frames of a filterbank call are interleaved per bin (bin k of frame t at k * TBF + t), so
 // pass 3 of the pair kernel stores both frames of a pair with one 64-bit store and the filterbank fetches
-// all frames of a bin with one vector load (k_front_pair; TB = TBF = 2 or 4).
-template <int TB, int MS_>
+// all frames of a bin with one vector load (k_front_pair; TBF = 2 or 4).  A tail batch of TB > TBF frames is
+// a row of such blocks: sub-batch h (a multiple of TBF) starts h * MS floats in.
+template <int TBF_, int MS_>
 struct MagInterleaved {
   static constexpr int MS = MS_;
-  static B2_HD int batch_offset(int h) { return h; }
+  static B2_HD int batch_offset(int h) { return h * MS_; }
   template <int TBF>
   static B2_HD void load(const float *mags, int k, float (&m)[TBF]) {
-    static_assert(TBF == TB && (TB == 2 || TB == 4), "one vector per bin");
-    if (TB == 2) {
+    static_assert(TBF == TBF_ && (TBF == 2 || TBF == 4), "one vector per bin");
+    if (TBF == 2) {
       const float2 v = *reinterpret_cast<const float2 *>(mags + k * 2);
       m[0] = v.x;
       m[1] = v.y;
@@ -56,42 +57,6 @@ struct MagInterleaved {
       m[TBF > 2 ? 2 : 0] = v.z;
       m[TBF > 2 ? 3 : 0] = v.w;
     }
-  }
-};
-// MagPairPlanes: four-frame tail batches of the pair kernel -- one plane per PAIR of frames, the two frames of
-// a pair interleaved per bin (bin k of frame t at (t / 2) * 2 MS + 2 k + (t & 1)).  Pass 3 stores a pair with
-// one 64-bit store at an 8-byte lane stride (conflict free; frames interleaved four-wide make that store
-// two-way conflicted), the filterbank fetches a bin's four frames with two 64-bit loads.
-template <int MS_>
-struct MagPairPlanes {
-  static constexpr int MS = MS_;
-  static B2_HD int batch_offset(int h) { return h; }
-  template <int TBF>
-  static B2_HD void load(const float *mags, int k, float (&m)[TBF]) {
-    static_assert(TBF == 4, "two planes of two frames");
-    const float2 a = *reinterpret_cast<const float2 *>(mags + 2 * k);
-    const float2 b = *reinterpret_cast<const float2 *>(mags + 2 * MS_ + 2 * k);
-    m[0] = a.x;
-    m[1] = a.y;
-    m[TBF > 2 ? 2 : 0] = b.x;
-    m[TBF > 2 ? 3 : 0] = b.y;
-  }
-};
-// MagInPlace: k_front_pair for frame 4096 has no room for a separate magnitude buffer; pass 3 overwrites
-// the FFT columns it has just consumed: bin k = q + 256 j of frames (A, B) sits at floats
-// 2 * column_offset(q) + 2 j + {0, 1} of the pair's buffer (F2 = 2 * frame size).  Both frames come with
-// one 64-bit load.
-template <int F2, int MS_>
-struct MagInPlace {
-  static constexpr int MS = MS_;
-  static B2_HD int batch_offset(int) { return 0; }
-  static B2_HD int at(int k) { return 2 * fft_col_offset<F2>(k & 255) + 2 * (k >> 8); }
-  template <int TBF>
-  static B2_HD void load(const float *mags, int k, float (&m)[TBF]) {
-    static_assert(TBF == 2, "in-place magnitudes hold exactly one pair of frames");
-    const float2 v = *reinterpret_cast<const float2 *>(mags + at(k));
-    m[0] = v.x;
-    m[1] = v.y;
   }
 };
 

@@ -49,6 +49,8 @@ struct FftCfg {
   static constexpr int S1 = BPF + 1;       // buf1 row stride (float2), +1 keeps pass-2 reads conflict free
   static constexpr int BUF = 16 * S1;      // float2 elements of the single in-place buffer of a frame
   static constexpr int TW3 = 129 * R3;     // tw3[n3*129 + q] = W_N^(n3*q), q in [0,128]
+  static constexpr int LOG2R3 = (R3 == 2) ? 1 : (R3 == 4) ? 2 : (R3 == 8) ? 3 : 4;
+  static constexpr int TW3C = 129 * LOG2R3; // compact form (pair kernels): row r holds n3 = 2^r -- the only rows tw3_rows reads
   static constexpr int PT = 129 * R3;      // pt[k3*129 + q] = -i * W_F^(q + 256*k3)
   static constexpr int WR = 2 * R3;        // wr[e] = W_(2 R3)^e, used by the self-paired columns
   // frames per tail batch (filterbank/log/diff stage): 4, 4, 2, 1 -- measured best on B200 (profiles/README.md)
@@ -267,21 +269,28 @@ B2_HD constexpr int fft_col_offset(int q) {
 // products -- shared-memory wavefronts, not FP32 issue slots, are the scarcer resource in these kernels
 // (profiles/README.md); the extra rounding (<= 3 products deep) is ~2e-7 relative.  -DB2_TW3_TABLE reads
 // all R3-1 rows instead.
-template <int R3>
+// COMPACT: the table holds only the rows n3 = 1, 2, 4, 8 (row r = log2 n3), which is all this routine reads --
+// the pair kernels keep it that way in shared memory (FftCfg::TW3C).
+template <int R3, bool COMPACT = false>
 B2_HD void tw3_rows(const float2 *tw3q, float2 (&w)[R3]) {
 #if defined(B2_TW3_TABLE)
+  if (!COMPACT) {
 #pragma unroll
-  for (int n3 = 1; n3 < R3; ++n3) w[n3] = tw3q[n3 * 129];
-#else
+    for (int n3 = 1; n3 < R3; ++n3) w[n3] = tw3q[n3 * 129];
+    return;
+  }
+#endif
+  {
+    int r = 0;
 #pragma unroll
-  for (int n3 = 1; n3 < R3; n3 *= 2) w[n3] = tw3q[n3 * 129];
+    for (int n3 = 1; n3 < R3; n3 *= 2, ++r) w[n3] = tw3q[(COMPACT ? r : n3) * 129];
+  }
 #pragma unroll
   for (int n3 = 3; n3 < R3; ++n3)
     if (n3 & (n3 - 1)) {
       const int hi = n3 >= 8 ? 8 : n3 >= 4 ? 4 : 2;
       w[n3] = cmul(w[hi], w[n3 - hi]);
     }
-#endif
 }
 
 // cos / sin of j pi / 16, j in [0,16): W_(2 R3)^k3 = (cos_pi16(j), -sin_pi16(j)) with j = k3 * 16 / R3
@@ -411,6 +420,7 @@ B2_HD float2 fft_pass3_selfpaired(int lane, const float2 *buf, const float2 *wr,
 // -------------------------------------------------------------------------------------------------
 // unit u in [0,127]: pa / pb = columns u and (256-u)&255 (u = 0 pairs column 0 with itself and simply
 // emits bins 256 j twice, plus bin F/2 which lands in the padding of the magnitude buffer).
+// tw3u = compact twiddle table + u: tw3c[r*129 + q] = W_N^(2^r q), r < log2 R3.
 // emit(bin, |XA[bin]|, |XB[bin]|) -- the caller takes the magnitudes.
 template <int F2, class Emit>
 B2_HD void fft_pair_pass3_unit(int u, const float2 *pa, const float2 *pb, const float2 *tw3u, Emit emit) {
@@ -426,7 +436,7 @@ B2_HD void fft_pair_pass3_unit(int u, const float2 *pa, const float2 *pb, const 
   }
   {
     float2 w[R3];
-    tw3_rows<R3>(tw3u, w);
+    tw3_rows<R3, true>(tw3u, w);     // tw3u: compact table (rows n3 = 1, 2, 4, 8)
 #pragma unroll
     for (int n3 = 1; n3 < R3; ++n3) {
       P[n3] = cmul(P[n3], w[n3]);

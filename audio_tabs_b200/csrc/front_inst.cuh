@@ -106,7 +106,27 @@ static cudaError_t launch_pair_size(int in, FrontParams &p, int num_sms, long lo
   return cudaErrorInvalidValue;
 }
 
+// groups per CTA of the one-launch kernel: its group blocks are sized for frame 4096 (33 KB FFT buffer + 16 KB magnitudes)
+constexpr int kMultiGroups = 3;
+
+template <int IN>
+static cudaError_t launch_multi_one(MultiParams &m, int num_sms, long long task_bound, cudaStream_t st) {
+  constexpr int G = kMultiGroups;
+  const size_t smem = multi_smem_layout(m, G);
+  if (smem > kMaxSmemPerCta) return cudaErrorInvalidConfiguration;
+  auto kern = k_front_multi<IN, G>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  long long ctas = (task_bound + G - 1) / G;
+  int grid = (int)(ctas < num_sms ? (ctas < 1 ? 1 : ctas) : num_sms);
+  kern<<<grid, kGroupThreads * G, smem, st>>>(m);
+  return cudaGetLastError();
+}
+
 }  // namespace b2
+
+// defined in front_multi.cu
+cudaError_t b2_launch_multi(int in, b2::MultiParams &m, int num_sms, long long task_bound, cudaStream_t st);
 
 cudaError_t b2_launch_pair_1024(int in, b2::FrontParams &p, int num_sms, long long task_bound, cudaStream_t st);
 cudaError_t b2_launch_pair_2048(int in, b2::FrontParams &p, int num_sms, long long task_bound, cudaStream_t st);

@@ -20,7 +20,6 @@
 
 #include "fb_core.cuh"
 #include "fft_core.cuh"
-#include "tma.cuh"
 
 namespace b2 {
 
@@ -36,6 +35,7 @@ struct FrontParams {
   const int *task_off;  // n_clips + 1 (workspace, written by k_setup_tasks)
   int *task_counter;    // workspace
   int chunk;            // frames per task
+  int frame_size;
   double hop;
   int origin;
   // tables (plan-owned, device)

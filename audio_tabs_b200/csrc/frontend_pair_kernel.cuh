@@ -8,6 +8,13 @@
 // /root/reference/backend/app/services/grid/beats.py:74 (RNNBeatProcessor):
 //   signal_frame -> frame*fft_window -> fftpack.fft[:F/2] -> np.abs -> np.dot(., filterbank)
 //   -> np.log10(mul*y+add) -> SpectrogramDifference(positive) -> np.hstack
+//
+// Two kernels are built from the same per-task routine (pair_run_task):
+//   k_front_pair<F, IN, G>   one resolution per launch (b200spec_logfilt)
+//   k_front_multi<IN, G>     up to three resolutions of one hop in ONE launch (b200spec_logfilt_multi): a group
+//                            takes a (clip, chunk of frames) task through every resolution in turn, so the
+//                            chunk's samples leave HBM once (the later resolutions find them in L2 / L1) and
+//                            all columns of its rows are written before the group moves on.
 #pragma once
 #include <type_traits>
 
@@ -15,70 +22,53 @@
 
 namespace b2 {
 
+// pairs of frames a group carries through one FFT step.  The default fills one step with 128 butterflies per
+// pass (one per thread) at frames 1024 / 2048 and 256 (two per thread, interleaved) at frame 4096.
 template <int F>
+struct PairPps {
+#ifndef B2_PAIR_PPS_1024
+#define B2_PAIR_PPS_1024 2
+#endif
+#ifndef B2_PAIR_PPS_2048
+#define B2_PAIR_PPS_2048 1
+#endif
+  static constexpr int value = (F == 1024) ? B2_PAIR_PPS_1024 : (F == 2048) ? B2_PAIR_PPS_2048 : 1;
+};
+
+template <int F, int PPS_ = PairPps<F>::value, int TBF_MAX = 4>
 struct PairCfg {
   static_assert(F == 1024 || F == 2048 || F == 4096, "pair transform: frame sizes 1024, 2048, 4096");
   using C2 = FftCfg<2 * F>;                       // geometry of the F-point complex FFT
-  static constexpr int PPS = C2::FPG;             // pairs per group step
+  static constexpr int PPS = PPS_;                // pairs per group step
   static constexpr int FPS = 2 * PPS;             // frames per group step
+  static constexpr int NB = PPS * C2::BPF;        // radix-16 butterflies per pass and step
+  static_assert(NB % kGroupThreads == 0, "a step must give every thread the same number of butterflies");
+  static constexpr int IT = NB / kGroupThreads;   // butterflies per thread and pass (1 or 2)
+  static_assert(IT == 1 || IT == 2, "one or two butterflies per thread");
+  // thread tid runs butterflies j = tid + it * 128 of the step: pair slot j / BPF, butterfly j % BPF
   static constexpr int TB = FftCfg<F>::TB >= FPS ? FftCfg<F>::TB : FPS;   // frames per tail batch (multiple of FPS)
-#ifdef B2_PAIR_TBF_2048   // tuning override: frames per filterbank / band-stage call at frame 2048
-  static constexpr int TBF = (F == 2048) ? B2_PAIR_TBF_2048 : (TB < 4 ? TB : 4);
-#else
-  static constexpr int TBF = TB < 4 ? TB : 4;
-#endif
+  static constexpr int TBF = TB < TBF_MAX ? TB : TBF_MAX;                 // frames per filterbank / band-stage call
   static constexpr int MS = FftCfg<F>::MS;        // floats per frame in the magnitude buffer
-  // Frame 4096: a 33 KB FFT buffer per pair plus 16 KB of magnitudes allow three groups per SM only.
-  // -DB2_PAIR_INPLACE makes pass 3 write the magnitudes IN PLACE of the columns it has consumed
-  // (MagInPlace) so that four groups fit; measured on B200 it loses (7.67 ms against 7.54 ms for three
-  // groups with 163 registers: the scattered addressing and the extra barrier cost more than the fourth
-  // group brings), so it is off by default.
-#ifdef B2_PAIR_INPLACE
-  static constexpr bool INPLACE = (F == 4096);
-#else
-  static constexpr bool INPLACE = false;
-#endif
-#ifdef B2_PAIR_MAG_LINEAR   // tuning: one row of MS floats per frame instead of frames interleaved per bin
-  using MA = typename std::conditional<INPLACE, MagInPlace<2 * F, MS>, MagLinear<MS>>::type;
-  static constexpr bool INTERLEAVED = false;
-  static constexpr bool PLANES = false;
-#else
-  static constexpr bool INTERLEAVED = !INPLACE && (TB == TBF) && (TB == 2 || TB == 4);
-#ifdef B2_PAIR_MAG_PLANES   // four-frame batches: one plane per pair of frames (conflict-free pass-3 stores;
-                            // measured slower on B200: 2.14 / 3.56 against 2.09 / 3.55 ms at frames 1024 / 2048)
-  static constexpr bool PLANES = INTERLEAVED && TB == 4;
-#else
-  static constexpr bool PLANES = false;
-#endif
-  using MA = typename std::conditional<INPLACE, MagInPlace<2 * F, MS>,
-             typename std::conditional<PLANES, MagPairPlanes<MS>,
-             typename std::conditional<INTERLEAVED, MagInterleaved<TB, MS>, MagLinear<MS>>::type>::type>::type;
-#endif
-  // TMA staging: once pass 3 has consumed the FFT buffer, one thread starts a bulk copy (cp.async.bulk,
-  // completion on an mbarrier) of the raw samples the FIRST step of the next tail batch needs into that
-  // buffer; it lands while the filterbank / band stage runs, and pass 1 then reads shared memory instead
-  // of waiting for L2.  float32 mono only (the copy is byte-wise); the span of all FPS frames of a step
-  // must fit the PPS * BUF complex slots of the buffer.  Measured on B200 (config 2): frame 4096 unchanged
-  // (7.14 ms with and without: the other groups already cover the L2 latency), frames 1024 / 2048 5 % / 4 %
-  // slower (the extra barrier between reading the raw samples and overwriting them), so it is compiled in
-  // only with -DB2_PAIR_TMA.
-#ifdef B2_PAIR_TMA
-  static constexpr bool TMA = true;
-#else
-  static constexpr bool TMA = false;
-#endif
-  static_assert(TB % FPS == 0, "tail batch must hold whole FFT steps");
-  static_assert(!INPLACE || (TB == FPS && PPS == 1), "in-place magnitudes: one pair per tail batch");
+  // frames of a filterbank call interleaved per bin (one 64-bit store per pair in pass 3, one vector load per
+  // bin in the filterbank); sub-batch h of a longer tail batch starts h * MS floats in
+  static constexpr bool INTERLEAVED = (TBF == 2 || TBF == 4);
+  using MA = typename std::conditional<INTERLEAVED, MagInterleaved<TBF, MS>, MagLinear<MS>>::type;
+  // offset between the two pass-2 butterflies of a thread (IT == 2): the next 128 butterflies are either in the
+  // same pair (BPF = 256: columns n3 + 8) or in a later pair slot
+  static constexpr int D2 = (C2::BPF > kGroupThreads) ? (kGroupThreads >> 4) : (kGroupThreads / C2::BPF) * C2::BUF;
+  static_assert(TB % FPS == 0 && TB % TBF == 0, "tail batch must hold whole FFT steps and whole filterbank calls");
 };
 
+// byte offsets of one resolution's tables, starting at `o`; returns the end.  with_window = false leaves the
+// window in global memory (o_win = -1): the pair kernel only reads the table at clip edges and for windows
+// that are not np.hanning (FrontParams::win_fly).
 template <int F>
-inline size_t pair_smem_layout(FrontParams &p, int G) {
-  using P = PairCfg<F>;
-  using C2 = typename P::C2;
+inline size_t pair_table_layout(FrontParams &p, size_t o, bool with_window) {
+  using C2 = FftCfg<2 * F>;
   auto al = [](size_t v) { return (v + 15) & ~size_t(15); };
-  size_t o = 0;
-  p.o_win = (int)o; o = al(o + sizeof(float) * F);
-  p.o_tw3 = (int)o; o = al(o + sizeof(float2) * C2::TW3);
+  p.o_win = -1;
+  if (with_window) { p.o_win = (int)o; o = al(o + sizeof(float) * F); }
+  p.o_tw3 = (int)o; o = al(o + sizeof(float2) * C2::TW3C);
   p.o_pt = (int)o;                                 // no split twiddles
   p.o_wr = (int)o;  o = al(o + sizeof(float2) * C2::WR);
   p.part_stride = p.fb_ns * kGroupThreads * 4;
@@ -86,46 +76,268 @@ inline size_t pair_smem_layout(FrontParams &p, int G) {
   p.o_band = (int)o; o = al(o + sizeof(int4) * (p.num_bands > 0 ? p.num_bands : 1));
   p.o_dw = (int)o;   o = al(o + sizeof(float) * (p.fb_ndw > 0 ? p.fb_ndw : 1));
   p.o_proj = (int)o; o = al(o + proj_table_bytes(p));
-  p.o_groups = (int)o;
+  return o;
+}
+
+// byte offsets inside a group's block; returns its size
+template <class P>
+inline size_t pair_group_layout(FrontParams &p) {
+  using C2 = typename P::C2;
+  auto al = [](size_t v) { return (v + 15) & ~size_t(15); };
   size_t g = 0;
   g = al(g + sizeof(float2) * P::PPS * C2::BUF);   // in-place FFT buffers (one per pair)
   p.mag_stride = P::MS;
-  p.g_mags = 0;         // in place: the magnitudes live in the FFT buffer
-  if (!P::INPLACE) { p.g_mags = (int)g; g = al(g + sizeof(float) * P::TB * P::MS); }
+  p.g_mags = (int)g;    g = al(g + sizeof(float) * P::TB * P::MS);
   p.g_partial = (int)g; g = al(g + sizeof(float) * P::TBF * p.part_stride);
   p.g_hist = (int)g;    g = al(g + sizeof(float) * (p.diff_frames > 0 ? p.diff_frames : 1) * p.num_bands);
-  p.g_lrow = (int)g;    g = al(g + sizeof(float) * P::TBF * p.num_bands);
+  p.g_lrow = (int)g;    g = al(g + (p.num_classes > 0 ? sizeof(float) * P::TBF * p.num_bands : 0));   // rows for the projection only
   p.g_red = (int)g;     g = al(g + sizeof(float) * 4 * P::TBF);
   p.g_task = (int)g;    g = al(g + 16);
-  p.group_bytes = (int)g;
-  return o + g * G;
+  return g;
+}
+
+template <int F>
+inline size_t pair_smem_layout(FrontParams &p, int G) {
+  const size_t o = pair_table_layout<F>(p, 0, true);
+  p.o_groups = (int)o;
+  p.group_bytes = (int)pair_group_layout<PairCfg<F>>(p);
+  return o + (size_t)p.group_bytes * G;
+}
+
+// ---- all resolutions of one hop in one launch: parameters and shared-memory plan ---------------------------------------
+constexpr int kMultiMaxRes = 3;
+struct MultiParams {
+  int n_res;
+  FrontParams r[kMultiMaxRes];   // sig / clip_off / frame_off / n_clips / task_off / task_counter / chunk are the same in all
+};
+
+// geometry of a resolution inside k_front_multi: every step fills the group's 33 KB FFT buffer at frames 4096
+// (one pair) and 2048 (two pairs) with two butterflies per thread and pass; frame 1024 keeps two pairs per step
+// (four would need an eight-frame magnitude buffer).  Frames 2048 / 4096 run two frames per filterbank call,
+// which keeps the partial sums at 4 KB.
+template <int F>
+struct MultiCfg {
+  using type = PairCfg<F, (F == 4096) ? 1 : 2, (F == 1024) ? 4 : 2>;
+};
+
+// tables of every resolution side by side (windows stay in global memory), then G group blocks sized for the
+// largest resolution
+inline size_t multi_smem_layout(MultiParams &m, int G) {
+  size_t o = 0, gb = 0;
+  for (int i = 0; i < m.n_res; ++i) {
+    FrontParams &p = m.r[i];
+    size_t g = 0;
+    switch (p.frame_size) {
+      case 1024: o = pair_table_layout<1024>(p, o, false); g = pair_group_layout<MultiCfg<1024>::type>(p); break;
+      case 2048: o = pair_table_layout<2048>(p, o, false); g = pair_group_layout<MultiCfg<2048>::type>(p); break;
+      default: o = pair_table_layout<4096>(p, o, false); g = pair_group_layout<MultiCfg<4096>::type>(p); break;
+    }
+    if (g > gb) gb = g;
+  }
+  for (int i = 0; i < m.n_res; ++i) {
+    m.r[i].o_groups = (int)o;
+    m.r[i].group_bytes = (int)gb;
+    m.r[i].g_task = (int)gb - 16;      // the task slot is shared by all resolutions: the last 16 bytes of the block
+  }
+  return o + gb * G;
 }
 
 #if defined(__CUDACC__)
 
-template <int F, int IN, int G>
-__global__ void __launch_bounds__(kGroupThreads *G, 1) k_front_pair(const FrontParams p) {
-  using P = PairCfg<F>;
-  using C2 = typename P::C2;
-  constexpr int F2 = 2 * F, PPS = P::PPS, FPS = P::FPS, R3 = C2::R3, S1 = C2::S1, TB = P::TB, TBF = P::TBF, MS = P::MS;
-  extern __shared__ __align__(16) unsigned char smem[];
-  float *s_win = reinterpret_cast<float *>(smem + p.o_win);
+// copies one resolution's tables into shared memory (all threads of the CTA; the caller syncs afterwards)
+template <int F>
+__device__ __forceinline__ void pair_stage_tables(const FrontParams &p, unsigned char *smem) {
+  using C2 = FftCfg<2 * F>;
+  if (p.o_win >= 0) {
+    float *s_win = reinterpret_cast<float *>(smem + p.o_win);
+    for (int i = threadIdx.x; i < F; i += blockDim.x) s_win[i] = p.window[i];
+  }
   float2 *s_tw3 = reinterpret_cast<float2 *>(smem + p.o_tw3);
   float2 *s_wr = reinterpret_cast<float2 *>(smem + p.o_wr);
   float4 *s_w4 = reinterpret_cast<float4 *>(smem + p.o_w4);
   int4 *s_band = reinterpret_cast<int4 *>(smem + p.o_band);
   float *s_dw = reinterpret_cast<float *>(smem + p.o_dw);
-
-  for (int i = threadIdx.x; i < F; i += blockDim.x) s_win[i] = p.window[i];
-  for (int i = threadIdx.x; i < C2::TW3; i += blockDim.x) s_tw3[i] = p.tw3[i];   // F-point tables (pair_tw3 / pair_wr)
+  for (int i = threadIdx.x; i < C2::TW3C; i += blockDim.x) s_tw3[i] = p.tw3[i];   // F-point tables (pair_tw3 / pair_wr)
   for (int i = threadIdx.x; i < C2::WR; i += blockDim.x) s_wr[i] = p.wr[i];
   if (!p.fb_w4_global)
     for (int i = threadIdx.x; i < p.fb_ns * p.fb_L * kGroupThreads; i += blockDim.x) s_w4[i] = p.fb_w4[i];
   for (int i = threadIdx.x; i < p.num_bands; i += blockDim.x) s_band[i] = p.fb_band[i];
   for (int i = threadIdx.x; i < p.fb_ndw; i += blockDim.x) s_dw[i] = p.fb_dw[i];
   TailCtx::stage_proj(p, smem);
+}
+
+// One task -- frames [f0, f1) of clip c -- of one resolution, run by the 128 threads of group g.
+// ZERO_PAD: the magnitude buffer may hold another resolution's data (k_front_multi): its padding, which
+// zero-weight filterbank taps read, is cleared first.
+template <class P, int F, int IN, bool ZERO_PAD>
+__device__ __forceinline__ void pair_run_task(const FrontParams &p, unsigned char *smem, unsigned char *gmem, int g, int tid,
+                                              const float2 (&tw2r)[16], int c, int f0, int f1) {
+  using C2 = typename P::C2;
+  constexpr int F2 = 2 * F, PPS = P::PPS, FPS = P::FPS, R3 = C2::R3, S1 = C2::S1, TB = P::TB, TBF = P::TBF, MS = P::MS;
+  constexpr int IT = P::IT, BPF = C2::BPF;
+  const float *win = p.o_win >= 0 ? reinterpret_cast<const float *>(smem + p.o_win) : p.window;
+  const float2 *s_tw3 = reinterpret_cast<const float2 *>(smem + p.o_tw3);
+  const float2 *s_wr = reinterpret_cast<const float2 *>(smem + p.o_wr);
+  float2 *buf = reinterpret_cast<float2 *>(gmem);
+  float *s_mags = reinterpret_cast<float *>(gmem + p.g_mags);
+  TailCtx tctx{reinterpret_cast<const float4 *>(smem + p.o_w4), reinterpret_cast<const int4 *>(smem + p.o_band),
+               reinterpret_cast<const float *>(smem + p.o_dw), s_mags, reinterpret_cast<float *>(gmem + p.g_partial),
+               reinterpret_cast<float *>(gmem + p.g_hist), reinterpret_cast<float *>(gmem + p.g_lrow),
+               reinterpret_cast<float *>(gmem + p.g_red), g, tid};
+  tctx.resolve(p);
+
+  // butterflies of this thread in passes 1 and 2: j = tid + it * 128 -> (pair slot, butterfly)
+  const int sl0 = tid / BPF, b0 = tid % BPF;                            // it = 0
+  constexpr int SL_STEP = (BPF > kGroupThreads) ? 0 : kGroupThreads / BPF;     // slot / butterfly advance of it = 1
+  constexpr int B_STEP = (BPF > kGroupThreads) ? kGroupThreads : 0;
+  float2 *p2 = buf + sl0 * C2::BUF + (b0 & 15) * S1 + (b0 >> 4);        // pass-2 in-place base (k1, n3) of it = 0
+  float2 wab0 = make_float2(0.f, 0.f), wab1 = wab0;                     // Hann window in registers (FrontParams::win_fly)
+  if (p.win_fly) {
+    wab0 = __ldg(p.win_ab + b0);
+    wab1 = (B_STEP > 0) ? __ldg(p.win_ab + b0 + B_STEP) : wab0;
+  }
+  const int u = tid;                                                    // pass-3 unit (0..127, all active)
+  const int pa_off = fft_col_offset<F2>(u), pb_off = fft_col_offset<F2>((256 - u) & 255);
+
+  const int kd = p.diff_frames;
+  const long long samp0 = p.clip_off[c];
+  const long long nsamp = p.clip_off[c + 1] - samp0;
+  const long long row0 = p.frame_off[c];
+  const int fs = kd > 0 ? max(0, f0 - kd) : f0;              // warm-up rows for the difference
+  Samples<IN> S{clip_base<IN>(p.sig, samp0)};
+  float cscale = p.clip_scale != nullptr ? __ldg(p.clip_scale + c) : 1.f;
+  if (p.power) cscale *= cscale;         // a power spectrogram scales with the gain squared
+  int nonfinite = 0;
+
+  if (ZERO_PAD) {                        // bins N + 1 .. N + 15 of every frame of the batch (bin N is written by pass 3)
+    constexpr int N = F / 2, NPAD = MS - N - 1;
+    for (int i = tid; i < NPAD * TB; i += kGroupThreads) {
+      const int fi = i / NPAD, k = N + 1 + i % NPAD;
+      if (P::INTERLEAVED) s_mags[(fi / TBF) * TBF * MS + k * TBF + fi % TBF] = 0.f;
+      else s_mags[fi * MS + k] = 0.f;
+    }
+  }
+
+  int hslot = kd > 0 ? fs % kd : 0;                          // difference ring slot of frame fb
+  for (int fb = fs; fb < f1; fb += TB) {
+    // =============== FFT of the TB frames of this tail batch, FPS frames (PPS pairs) per step ===============
+#pragma unroll 1
+    for (int sub = 0; sub < TB; sub += FPS) {
+      const int f = fb + sub;
+      if (f >= f1) break;
+      // ---------------- pass 1: z[n] = w[n] (xA[n] + i xB[n]), DFT16 ----------------
+#pragma unroll 1
+      for (int it = 0; it < IT; ++it) {
+        const int sl = sl0 + it * SL_STEP, b = b0 + it * B_STEP;
+        const int fA = f + 2 * sl;                           // frames of this butterfly's pair (fB = fA + 1)
+        if (fA >= f1) break;
+        const long long sA = (long long)((double)fA * p.hop) - (F / 2) - p.origin;
+        const long long sB = (long long)((double)(fA + 1) * p.hop) - (F / 2) - p.origin;
+        const bool hasB = fA + 1 < f1;
+        const bool interior = (sA >= 0) && (sB + F <= nsamp) && hasB;     // sB >= sA
+        float2 *p1 = buf + sl * C2::BUF + b;                 // pass-1 store base
+        const float *wp = win + b;                           // window value of this butterfly's n1 = 0
+        if (interior && p.win_fly) {
+          const void *qa = S.ptr(sA + b), *qb = S.ptr(sB + b);
+          const float2 ab = it ? wab1 : wab0;
+          fft_pass1<F2>([&](int n1) {
+            const float w = fmaf(ab.x, p.win_cs[n1].x, fmaf(ab.y, p.win_cs[n1].y, p.win_h));
+            return crscale(make_float2(Samples<IN>::at_ptr(qa, n1 * BPF), Samples<IN>::at_ptr(qb, n1 * BPF)), w);
+          }, p1);
+        } else if (interior) {
+          const void *qa = S.ptr(sA + b), *qb = S.ptr(sB + b);
+          fft_pass1<F2>([&](int n1) {
+            const float w = wp[n1 * BPF];
+            return crscale(make_float2(Samples<IN>::at_ptr(qa, n1 * BPF), Samples<IN>::at_ptr(qb, n1 * BPF)), w);
+          }, p1);
+        } else {
+          fft_pass1<F2>([&](int n1) {
+            const float w = wp[n1 * BPF];
+            const long long a = sA + n1 * BPF + b, bb = sB + n1 * BPF + b;
+            const float xa = (a >= 0 && a < nsamp) ? S.at(a) : 0.f;
+            const float xb = (hasB && bb >= 0 && bb < nsamp) ? S.at(bb) : 0.f;
+            return crscale(make_float2(xa, xb), w);
+          }, p1);
+        }
+      }
+      if (tid < 32) {
+        // one warp pulls the samples that only the NEXT step's frames touch into L1, so pass 1 does not wait on
+        // L2 / HBM.  (Requesting the step after that into L2 as well, for the chord / key rates whose frames barely
+        // overlap, was measured on B200 and LOSES: config 3b 3.36 ms against 3.17 ms.)
+        constexpr int ESZ = (IN == IN_F32_MONO) ? 4 : (IN == IN_F32_STEREO) ? 8 : (IN == IN_I16_MONO) ? 2 : 4;
+        const long long e0 = ((long long)((double)(f + FPS - 1) * p.hop) + (F / 2) - p.origin) * ESZ;
+        long long e1 = ((long long)((double)(f + 2 * FPS - 1) * p.hop) + (F / 2) - p.origin) * ESZ;
+        if (e1 > nsamp * ESZ) e1 = nsamp * ESZ;
+        const char *bytes = reinterpret_cast<const char *>(S.base);
+        for (long long a = (e0 & ~127LL) + tid * 128; a < e1; a += 32 * 128)
+          if (a >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(bytes + a));
+      }
+      group_bar(g);
+      // ---------------- pass 2: twiddle, DFT16, in place ----------------
+      // two butterflies per thread: both with their loads issued together (the kernels are latency bound, not
+      // throughput bound: -1.9 % at frame 4096 on B200)
+      if (f + 2 * sl0 < f1) {
+        if (IT == 2 && f + 2 * (sl0 + SL_STEP) < f1) fft_pass2_x2<F2>(tw2r, p2, P::D2);
+        else fft_pass2<F2>(tw2r, p2);
+      }
+      group_bar(g);
+      // ---------------- pass 3: last radix on (column u + conj column 256-u): both frames' magnitudes ----------------
+#pragma unroll 1
+      for (int sl = 0; sl < PPS; ++sl) {
+        if (f + 2 * sl >= f1) break;
+        const float2 *fbuf = buf + sl * C2::BUF;
+        const int fi = sub + 2 * sl;                         // index of frame A inside the tail batch
+        float *magsA = P::INTERLEAVED ? s_mags + (fi / TBF) * TBF * MS + fi % TBF : s_mags + fi * MS;
+        auto put = [&](int bin, float ma, float mb) {
+          if (P::INTERLEAVED) {            // frames fi and fi + 1 sit side by side
+            *reinterpret_cast<float2 *>(magsA + bin * TBF) = make_float2(ma, mb);
+          } else {
+            magsA[bin] = ma;
+            magsA[MS + bin] = mb;
+          }
+        };
+        fft_pair_pass3_unit<F2>(u, fbuf + pa_off, fbuf + pb_off, s_tw3 + u,
+                                [&](int bin, float2 xa, float2 xb) { put(bin, cabs_fast(xa), cabs_fast(xb)); });
+        if (tid < 32) {          // the self-paired column 128: one bin per lane, mirror bin by shuffle
+          const int k3 = tid & (R3 - 1);
+          constexpr int NPART = kCol128Parts<F2>;                     // R3 * NPART <= 32 lanes share the sum
+          float2 Z = make_float2(0.f, 0.f);
+          if (tid < R3 * NPART) Z = fft_pair_col128_part<F2>(k3, tid / R3, fbuf, s_wr);
+#pragma unroll
+          for (int d = R3; d < R3 * NPART; d <<= 1) {
+            Z.x += __shfl_xor_sync(0xffffffffu, Z.x, d);
+            Z.y += __shfl_xor_sync(0xffffffffu, Z.y, d);
+          }
+          const float zx = __shfl_sync(0xffffffffu, Z.x, R3 - 1 - k3), zy = __shfl_sync(0xffffffffu, Z.y, R3 - 1 - k3);
+          if (tid < R3 / 2)       // |Z + conj Z'| (frame A), |Z - conj Z'| (frame B)
+            put(128 + 256 * tid, cabs_fast(make_float2(Z.x + zx, Z.y - zy)), cabs_fast(make_float2(Z.x - zx, Z.y + zy)));
+        }
+      }
+      group_bar(g);   // pass-3 reads done before the next pass 1 overwrites buf; magnitudes visible
+    }
+    // =============== the tail of this batch ===============
+    hslot = front_tail<TB, TBF, typename P::MA>(p, tctx, fb, f0, f1, row0, hslot, cscale, nonfinite);
+  }
+  if (p.clip_status != nullptr && nonfinite) atomicOr(p.clip_status + c, 1);
+}
+
+// the clip that owns task `task`: task_off[c] <= task < task_off[c+1]
+__device__ __forceinline__ int task_clip(const int *task_off, int n_clips, int task) {
+  int lo = 0, hi = n_clips;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (task_off[mid] <= task) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+template <int F, int IN, int G>
+__global__ void __launch_bounds__(kGroupThreads *G, 1) k_front_pair(const FrontParams p) {
+  using P = PairCfg<F>;
+  extern __shared__ __align__(16) unsigned char smem[];
+  pair_stage_tables<F>(p, smem);
   for (int gi = 0; gi < G; ++gi)      // magnitudes (and their padding, which zero-weight taps may read) start out finite
-    for (int i = threadIdx.x; i < (P::INPLACE ? 2 * C2::BUF : TB * MS); i += blockDim.x)
+    for (int i = threadIdx.x; i < P::TB * P::MS; i += blockDim.x)
       reinterpret_cast<float *>(smem + p.o_groups + (size_t)gi * p.group_bytes + p.g_mags)[i] = 0.f;
   __syncthreads();
 
@@ -133,44 +345,11 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front_pair(const FrontP
   const int g = threadIdx.x / kGroupThreads;
   const int tid = ((((threadIdx.x >> 5) + g) & 3) << 5) | (threadIdx.x & 31);
   unsigned char *gmem = smem + p.o_groups + (size_t)g * p.group_bytes;
-  float2 *buf = reinterpret_cast<float2 *>(gmem);
-  float *s_mags = reinterpret_cast<float *>(gmem + p.g_mags);
   volatile int *s_task = reinterpret_cast<volatile int *>(gmem + p.g_task);
-  TailCtx tctx{s_w4, s_band, s_dw, s_mags, reinterpret_cast<float *>(gmem + p.g_partial),
-               reinterpret_cast<float *>(gmem + p.g_hist), reinterpret_cast<float *>(gmem + p.g_lrow),
-               reinterpret_cast<float *>(gmem + p.g_red), g, tid};
-  tctx.resolve(p);
-
-  // per-thread constants ---------------------------------------------------------------------
   float2 tw2r[16];                       // pass-2 twiddles of this thread's k1
 #pragma unroll
   for (int n2 = 0; n2 < 16; ++n2) tw2r[n2] = __ldg(&p.tw2[(tid & 15) * 16 + n2]);
-  const int sl12 = (PPS > 1) ? tid / C2::BPF : 0;           // pair slot this thread serves in pass 1/2
-  const int b12 = (PPS > 1) ? tid % C2::BPF : tid;          // butterfly index in pass 1/2 (first iteration)
-  float2 *p1 = buf + sl12 * C2::BUF + b12;                              // pass-1 store base
-  const float *w1 = s_win + b12;                                        // window value of this butterfly's n1 = 0
-  float2 wab0 = make_float2(0.f, 0.f), wab1 = wab0;                     // Hann window in registers (FrontParams::win_fly)
-  if (p.win_fly) {
-    wab0 = __ldg(p.win_ab + b12);
-    if (C2::IT12 > 1) wab1 = __ldg(p.win_ab + b12 + kGroupThreads);
-  }
-  float2 *p2 = buf + sl12 * C2::BUF + (b12 & 15) * S1 + (b12 >> 4);     // pass-2 in-place base (k1, n3)
-  const int u = tid;                                                    // pass-3 unit (0..127, all active)
-  const int pa_off = fft_col_offset<F2>(u), pb_off = fft_col_offset<F2>((256 - u) & 255);
-
   const int total_tasks = p.task_off[p.n_clips];
-  const int kd = p.diff_frames;
-  constexpr bool kTma = P::TMA && (IN == IN_F32_MONO);
-  const long long sig_bytes = kTma ? p.clip_off[p.n_clips] * 4 : 0;      // the packed buffer holds at least all clips
-  uint64_t *s_bar = reinterpret_cast<uint64_t *>(gmem + p.g_task + 8);   // one mbarrier per group
-  uint32_t bar_parity = 0;
-  bool staged = false;                   // the samples of the next step's frames are on their way into buf
-  int st_delta = 0;                      // offset (floats) of the first frame's first sample inside buf
-  long long st_s0 = 0;                   // sample index (in the clip) of that first sample
-  if (kTma) {
-    if (tid == 0) mbar_init(s_bar, 1);
-    group_bar(g);
-  }
 
   for (;;) {
     if (tid == 0) *s_task = atomicAdd(p.task_counter, 1);
@@ -178,196 +357,54 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front_pair(const FrontP
     const int task = *s_task;
     group_bar(g);
     if (task >= total_tasks) break;
-
-    int lo = 0, hi = p.n_clips;          // clip that owns this task: task_off[c] <= task < task_off[c+1]
-    while (hi - lo > 1) {
-      int mid = (lo + hi) >> 1;
-      if (p.task_off[mid] <= task) lo = mid; else hi = mid;
-    }
-    const int c = lo;
-    const long long samp0 = p.clip_off[c];
-    const long long nsamp = p.clip_off[c + 1] - samp0;
-    const long long row0 = p.frame_off[c];
-    const int T = (int)(p.frame_off[c + 1] - row0);
+    const int c = task_clip(p.task_off, p.n_clips, task);
+    const int T = (int)(p.frame_off[c + 1] - p.frame_off[c]);
     const int f0 = (task - p.task_off[c]) * p.chunk;
-    const int f1 = min(T, f0 + p.chunk);
-    const int fs = kd > 0 ? max(0, f0 - kd) : f0;            // warm-up rows for the difference
-    Samples<IN> S{clip_base<IN>(p.sig, samp0)};
-    float cscale = p.clip_scale != nullptr ? __ldg(p.clip_scale + c) : 1.f;
-    if (p.power) cscale *= cscale;       // a power spectrogram scales with the gain squared
-    int nonfinite = 0;
+    pair_run_task<P, F, IN, false>(p, smem, gmem, g, tid, tw2r, c, f0, min(T, f0 + p.chunk));
+  }
+}
 
-    int hslot = kd > 0 ? fs % kd : 0;                        // difference ring slot of frame fb
-    staged = false;                                          // (a task never ends with a copy in flight: fn + FPS <= f1)
-    for (int fb = fs; fb < f1; fb += TB) {
-      // =============== FFT of the TB frames of this tail batch, FPS frames (PPS pairs) per step ===============
-#pragma unroll 1
-      for (int sub = 0; sub < TB; sub += FPS) {
-        const int f = fb + sub;
-        if (f >= f1) break;
-        // ---------------- pass 1: z[n] = w[n] (xA[n] + i xB[n]), DFT16 ----------------
-        const int fA = f + 2 * sl12;                         // frames of this thread's pair (fB = fA + 1)
-        if (fA < f1) {
-          const long long sA = (long long)((double)fA * p.hop) - (F / 2) - p.origin;
-          const long long sB = (long long)((double)(fA + 1) * p.hop) - (F / 2) - p.origin;
-          const bool hasB = fA + 1 < f1;
-          const bool interior = (sA >= 0) && (sB + F <= nsamp) && hasB;     // sB >= sA
-          if (kTma && staged && sub == 0) {
-            // raw samples are in buf (TMA): take this thread's elements into registers, let the whole group
-            // finish reading, then transform and overwrite the buffer
-            mbar_wait(s_bar, bar_parity);
-            const float *raw = reinterpret_cast<const float *>(buf) + st_delta;
-            const float *ra = raw + (int)(sA - st_s0) + b12, *rb = raw + (int)(sB - st_s0) + b12;
-            float xa[16 * C2::IT12], xb[16 * C2::IT12];
+template <int IN, int G>
+__global__ void __launch_bounds__(kGroupThreads *G, 1) k_front_multi(const MultiParams m) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  for (int i = 0; i < m.n_res; ++i) {
+    const FrontParams &p = m.r[i];
+    if (p.frame_size == 1024) pair_stage_tables<1024>(p, smem);
+    else if (p.frame_size == 2048) pair_stage_tables<2048>(p, smem);
+    else pair_stage_tables<4096>(p, smem);
+  }
+  const FrontParams &p0 = m.r[0];
+  for (int i = threadIdx.x; i < (p0.group_bytes * G) / 4; i += blockDim.x)     // every group block starts out zero (finite)
+    reinterpret_cast<float *>(smem + p0.o_groups)[i] = 0.f;
+  __syncthreads();
+
+  const int g = threadIdx.x / kGroupThreads;
+  const int tid = ((((threadIdx.x >> 5) + g) & 3) << 5) | (threadIdx.x & 31);
+  unsigned char *gmem = smem + p0.o_groups + (size_t)g * p0.group_bytes;
+  volatile int *s_task = reinterpret_cast<volatile int *>(gmem + p0.g_task);
+  float2 tw2r[16];                       // pass-2 twiddles W_256^(n2 k1): the same for every frame size
 #pragma unroll
-            for (int it = 0; it < C2::IT12; ++it)
-#pragma unroll
-              for (int n1 = 0; n1 < 16; ++n1) {
-                xa[it * 16 + n1] = ra[it * kGroupThreads + n1 * C2::BPF];
-                xb[it * 16 + n1] = rb[it * kGroupThreads + n1 * C2::BPF];
-              }
-            group_bar(g);
-#pragma unroll
-            for (int it = 0; it < C2::IT12; ++it) {
-              const float *wp = w1 + it * kGroupThreads;
-              fft_pass1<F2>([&](int n1) {
-                const float w = wp[n1 * C2::BPF];
-                return crscale(make_float2(xa[it * 16 + n1], xb[it * 16 + n1]), w);
-              }, p1 + it * kGroupThreads);
-            }
-          } else
-#if defined(B2_P1_X2)
-          if (C2::IT12 == 2 && interior && p.win_fly) {     // both butterflies of this thread, loads issued together
-            const void *qa = S.ptr(sA + b12), *qb = S.ptr(sB + b12);
-            fft_pass1_x2<F2>(
-                [&](int n1) {
-                  const float w = fmaf(wab0.x, p.win_cs[n1].x, fmaf(wab0.y, p.win_cs[n1].y, p.win_h));
-                  return crscale(make_float2(Samples<IN>::at_ptr(qa, n1 * C2::BPF), Samples<IN>::at_ptr(qb, n1 * C2::BPF)), w);
-                },
-                [&](int n1) {
-                  const float w = fmaf(wab1.x, p.win_cs[n1].x, fmaf(wab1.y, p.win_cs[n1].y, p.win_h));
-                  return crscale(make_float2(Samples<IN>::at_ptr(qa, n1 * C2::BPF + kGroupThreads),
-                                             Samples<IN>::at_ptr(qb, n1 * C2::BPF + kGroupThreads)), w);
-                },
-                p1, kGroupThreads);
-          } else
-#endif
+  for (int n2 = 0; n2 < 16; ++n2) tw2r[n2] = __ldg(&p0.tw2[(tid & 15) * 16 + n2]);
+  const int total_tasks = p0.task_off[p0.n_clips];
+
+  for (;;) {
+    if (tid == 0) *s_task = atomicAdd(p0.task_counter, 1);
+    group_bar(g);
+    const int task = *s_task;
+    group_bar(g);
+    if (task >= total_tasks) break;
+    const int c = task_clip(p0.task_off, p0.n_clips, task);
+    const int T = (int)(p0.frame_off[c + 1] - p0.frame_off[c]);
+    const int f0 = (task - p0.task_off[c]) * p0.chunk;
+    const int f1 = min(T, f0 + p0.chunk);
 #pragma unroll 1
-          for (int it = 0; it < C2::IT12; ++it) {
-            const int b = b12 + it * kGroupThreads;
-            const float *wp = w1 + it * kGroupThreads;
-            if (interior && p.win_fly) {
-              const void *qa = S.ptr(sA + b), *qb = S.ptr(sB + b);
-              const float2 ab = it ? wab1 : wab0;
-              fft_pass1<F2>([&](int n1) {
-                const float w = fmaf(ab.x, p.win_cs[n1].x, fmaf(ab.y, p.win_cs[n1].y, p.win_h));
-                return crscale(make_float2(Samples<IN>::at_ptr(qa, n1 * C2::BPF), Samples<IN>::at_ptr(qb, n1 * C2::BPF)), w);
-              }, p1 + it * kGroupThreads);
-            } else if (interior) {
-              const void *qa = S.ptr(sA + b), *qb = S.ptr(sB + b);
-              fft_pass1<F2>([&](int n1) {
-                const float w = wp[n1 * C2::BPF];
-                return crscale(make_float2(Samples<IN>::at_ptr(qa, n1 * C2::BPF), Samples<IN>::at_ptr(qb, n1 * C2::BPF)), w);
-              }, p1 + it * kGroupThreads);
-            } else {
-              fft_pass1<F2>([&](int n1) {
-                const float w = wp[n1 * C2::BPF];
-                const long long a = sA + n1 * C2::BPF + b, bb = sB + n1 * C2::BPF + b;
-                const float xa = (a >= 0 && a < nsamp) ? S.at(a) : 0.f;
-                const float xb = (hasB && bb >= 0 && bb < nsamp) ? S.at(bb) : 0.f;
-                return crscale(make_float2(xa, xb), w);
-              }, p1 + it * kGroupThreads);
-            }
-          }
-        }
-        if (tid < 32) {
-          // one warp pulls the samples that only the NEXT step's frames touch into L1
-          constexpr int ESZ = (IN == IN_F32_MONO) ? 4 : (IN == IN_F32_STEREO) ? 8 : (IN == IN_I16_MONO) ? 2 : 4;
-          const long long e0 = ((long long)((double)(f + FPS - 1) * p.hop) + (F / 2) - p.origin) * ESZ;
-          long long e1 = ((long long)((double)(f + 2 * FPS - 1) * p.hop) + (F / 2) - p.origin) * ESZ;
-          if (e1 > nsamp * ESZ) e1 = nsamp * ESZ;
-          const char *bytes = reinterpret_cast<const char *>(S.base);
-          for (long long a = (e0 & ~127LL) + tid * 128; a < e1; a += 32 * 128)
-            if (a >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(bytes + a));
-        }
-        group_bar(g);
-        // ---------------- pass 2: twiddle, DFT16, in place ----------------
-        if (fA < f1) {
-          // frame 4096: both butterflies of the thread with their loads issued together (the kernels are latency
-          // bound, not throughput bound: -1.9 % on B200; -DB2_NO_P2_X2 restores the loop)
-#if !defined(B2_NO_P2_X2)
-          if (C2::IT12 == 2) fft_pass2_x2<F2>(tw2r, p2, kGroupThreads >> 4);
-          else
-#endif
-#pragma unroll 1
-          for (int it = 0; it < C2::IT12; ++it) fft_pass2<F2>(tw2r, p2 + it * (kGroupThreads >> 4));
-        }
-        group_bar(g);
-        // ---------------- pass 3: last radix on (column u + conj column 256-u): both frames' magnitudes ----------------
-#pragma unroll 1
-        for (int sl = 0; sl < PPS; ++sl) {
-          if (f + 2 * sl >= f1) break;
-          const float2 *fbuf = buf + sl * C2::BUF;
-          float *magsA = s_mags + (sub + 2 * sl) * MS, *magsB = magsA + MS;
-          auto put = [&](int bin, float ma, float mb) {
-            if (P::INPLACE) {
-              *reinterpret_cast<float2 *>(s_mags + MagInPlace<F2, MS>::at(bin)) = make_float2(ma, mb);
-            } else if (P::PLANES) {        // plane of this pair, frames A and B side by side
-              *reinterpret_cast<float2 *>(s_mags + (sub / 2 + sl) * 2 * MS + 2 * bin) = make_float2(ma, mb);
-            } else if (P::INTERLEAVED) {   // frames sub + 2 sl and the next one sit side by side
-              *reinterpret_cast<float2 *>(s_mags + bin * TB + sub + 2 * sl) = make_float2(ma, mb);
-            } else {
-              magsA[bin] = ma;
-              magsB[bin] = mb;
-            }
-          };
-          fft_pair_pass3_unit<F2>(u, fbuf + pa_off, fbuf + pb_off, s_tw3 + u,
-                                  [&](int bin, float2 xa, float2 xb) { put(bin, cabs_fast(xa), cabs_fast(xb)); });
-          if (tid < 32) {          // the self-paired column 128: one bin per lane, mirror bin by shuffle
-            const int k3 = tid & (R3 - 1);
-            constexpr int NPART = kCol128Parts<F2>;                     // R3 * NPART <= 32 lanes share the sum
-            float2 Z = make_float2(0.f, 0.f);
-            if (tid < R3 * NPART) Z = fft_pair_col128_part<F2>(k3, tid / R3, fbuf, s_wr);
-#pragma unroll
-            for (int d = R3; d < R3 * NPART; d <<= 1) {
-              Z.x += __shfl_xor_sync(0xffffffffu, Z.x, d);
-              Z.y += __shfl_xor_sync(0xffffffffu, Z.y, d);
-            }
-            const float zx = __shfl_sync(0xffffffffu, Z.x, R3 - 1 - k3), zy = __shfl_sync(0xffffffffu, Z.y, R3 - 1 - k3);
-            if (tid < R3 / 2)       // |Z + conj Z'| (frame A), |Z - conj Z'| (frame B)
-              put(128 + 256 * tid, cabs_fast(make_float2(Z.x + zx, Z.y - zy)), cabs_fast(make_float2(Z.x - zx, Z.y + zy)));
-          }
-        }
-        group_bar(g);   // pass-3 reads done before the next pass 1 overwrites buf; magnitudes visible
-      }
-      // =============== stage the next batch's first step (TMA), then the tail of this batch ===============
-      if (kTma) {
-        if (staged) bar_parity ^= 1;                         // the wait of this batch's first step is done
-        staged = false;
-        const int fn = fb + TB;                              // first frame of the next batch
-        if (fn + FPS <= f1) {
-          const long long s_first = (long long)((double)fn * p.hop) - (F / 2) - p.origin;
-          const long long s_last = (long long)((double)(fn + FPS - 1) * p.hop) - (F / 2) - p.origin;
-          const long long g0 = samp0 + s_first;              // index in the packed buffer
-          const int delta = (int)(g0 & 3);                   // the bulk copy starts on a 16-byte boundary
-          const long long bytes = ((s_last - s_first + F + delta + 3) & ~3LL) * 4;
-          if (s_first >= 0 && s_last + F <= nsamp && bytes <= (long long)sizeof(float2) * PPS * C2::BUF &&
-              (g0 - delta) * 4 + bytes <= sig_bytes && ((reinterpret_cast<uintptr_t>(p.sig) & 15) == 0)) {
-            staged = true;
-            st_delta = delta;
-            st_s0 = s_first;
-            if (tid == 0) {
-              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic accesses to buf are done (barrier)
-              mbar_expect_tx(s_bar, (uint32_t)bytes);
-              tma_load_1d(buf, reinterpret_cast<const float *>(p.sig) + (g0 - delta), (uint32_t)bytes, s_bar);
-            }
-          }
-        }
-      }
-      hslot = front_tail<TB, TBF, typename P::MA>(p, tctx, fb, f0, f1, row0, hslot, cscale, nonfinite);
-      if (P::INPLACE) group_bar(g);   // the band stage has read its magnitudes before pass 1 overwrites the buffer
+    for (int i = 0; i < m.n_res; ++i) {
+      const FrontParams &p = m.r[i];
+      if (p.frame_size == 1024) pair_run_task<typename MultiCfg<1024>::type, 1024, IN, true>(p, smem, gmem, g, tid, tw2r, c, f0, f1);
+      else if (p.frame_size == 2048) pair_run_task<typename MultiCfg<2048>::type, 2048, IN, true>(p, smem, gmem, g, tid, tw2r, c, f0, f1);
+      else pair_run_task<typename MultiCfg<4096>::type, 4096, IN, true>(p, smem, gmem, g, tid, tw2r, c, f0, f1);
+      group_bar(g);      // the band stage of this resolution has read its buffers before the next one reuses them
     }
-    if (p.clip_status != nullptr && nonfinite) atomicOr(p.clip_status + c, 1);
   }
 }
 

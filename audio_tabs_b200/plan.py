@@ -23,6 +23,7 @@ from . import _ffi
 from .filters import Filterbank
 
 SUPPORTED_FRAME_SIZES = (1024, 2048, 4096, 8192)
+ONE_LAUNCH_DEFAULT = False      # FrontEnd(one_launch=None): see DESIGN.md section 4 for the measurement behind the default
 
 
 def _digest(*arrays) -> str:
@@ -249,7 +250,7 @@ class FrontEnd:
     """
 
     def __init__(self, specs: Sequence[ResolutionSpec], device: int = 0, dtype: str = "f32", channels: int = 1,
-                 end: str = "normal", concurrent_streams: bool = False):
+                 end: str = "normal", concurrent_streams: bool = False, one_launch: Optional[bool] = None):
         self.specs = list(specs)
         hops = {s.hop_size for s in self.specs}
         if len(hops) != 1:
@@ -270,6 +271,16 @@ class FrontEnd:
         self._streams = None
         self._events = None
         self.concurrent_streams = concurrent_streams and len(self.specs) > 1
+        # all resolutions in ONE launch (b200spec_logfilt_multi: each chunk's samples leave HBM once): needs 2-3
+        # resolutions of frame size <= 4096 whose tables fit one SM together, and no SuperFlux second pass.
+        # None = the library default (ONE_LAUNCH_DEFAULT); True raises if the plan cannot run that way.
+        res_idx = (C.c_int32 * len(self.specs))(*range(len(self.specs)))
+        can = (1 < len(self.specs) <= 3 and not any((s.diff_max_bins or 0) > 1 and s.diff_frames > 0 for s in self.specs)
+               and bool(self._lib.b200spec_logfilt_multi_supported(self.plan.handle, len(self.specs), res_idx)))
+        if one_launch and not can:
+            raise ValueError("these resolutions cannot run in one launch (2-3 resolutions of frame size <= 4096 sharing "
+                             "hop_size, tables within one SM's shared memory, no diff_max_bins)")
+        self.one_launch = can and (ONE_LAUNCH_DEFAULT if one_launch is None else bool(one_launch))
 
     # ---- helpers ---------------------------------------------------------------------------
     def _workspace(self, res: int, n_clips: int) -> torch.Tensor:
@@ -335,6 +346,33 @@ class FrontEnd:
                                  or not out.is_contiguous()):
             raise ValueError("out must be a contiguous float32 (total_frames, %d) tensor" % self.width)
         cur = torch.cuda.current_stream(self.device)
+        if self.one_launch:
+            n = len(self.specs)
+            ods = (_ffi.OutDesc * n)()
+            for r, s in enumerate(self.specs):
+                od = ods[r]
+                od.d_out = out.data_ptr() if out is not False else None
+                od.ld_out = self.width
+                od.col_spec = self.col[r]
+                od.col_diff = self.col[r] + s.num_bands if s.diff_frames > 0 else -1
+                od.d_flux = flux[r].data_ptr() if flux is not None and flux[r] is not None else None
+                od.d_proj = proj[r].data_ptr() if proj is not None and proj[r] is not None else None
+                od.ld_proj = proj[r].shape[1] if proj is not None and proj[r] is not None else 0
+                od.d_clip_scale = clip_scale.data_ptr() if clip_scale is not None else None
+                od.d_clip_status = clip_status.data_ptr() if clip_status is not None else None
+            ws = self._workspace(0, packed.n_clips)
+            if timing is not None:
+                t0 = torch.cuda.Event(enable_timing=True)
+                t0.record(cur)
+            _ffi.check(self._lib.b200spec_logfilt_multi(
+                self.plan.handle, n, (C.c_int32 * n)(*range(n)), _ptr(packed.sig), _ptr(packed.clip_off),
+                _ptr(packed.frame_off), packed.n_clips, packed.total_frames, ods, _ptr(ws), ws.numel(),
+                C.c_void_p(cur.cuda_stream)))
+            if timing is not None:
+                t1 = torch.cuda.Event(enable_timing=True)
+                t1.record(cur)
+                timing.append((-1, t0, t1))
+            return out
         use_side = self.concurrent_streams and packed.total_frames > 0
         side = self._side_streams() if use_side else None
         if use_side:

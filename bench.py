@@ -429,7 +429,8 @@ def run_ours(args, rank, world, local_rank):
     n_clips = args.clips
     n_samples = int(args.clip_seconds * SR)
     specs = beat_specs()
-    fe = FrontEnd(specs, device=local_rank, dtype="f32", channels=1, concurrent_streams=args.concurrent_streams)
+    fe = FrontEnd(specs, device=local_rank, dtype="f32", channels=1, concurrent_streams=args.concurrent_streams,
+                  one_launch=(True if args.one_launch else False if args.three_launches else None))
     sig = synth_batch_device(n_clips, n_samples, seed=2000 + rank, device=dev)
     packed = Packed(sig, [n_samples] * n_clips, fe.hop_size)
     out = fe.alloc_output(packed.total_frames)
@@ -482,21 +483,32 @@ def run_ours(args, rank, world, local_rank):
     peak, peak_src = load_peaks()
     traffic = load_traffic()
     per_kernel = []
-    for r, s in enumerate(specs):
-        ms = float(np.mean([a.elapsed_time(b) for rr, a, b in launch_events if rr == r]))
-        alg = in_bytes + packed.total_frames * s.out_width * 4
-        flops = packed.total_frames * (2.5 * s.frame_size * np.log2(s.frame_size) + s.frame_size
-                                       + 4 * s.frame_size / 2 + 2 * len(s.filterbank.banded()[3]) + 3 * s.num_bands)
-        per_kernel.append({"frame_size": s.frame_size, "ms": ms, "alg_bytes": alg, "gbs": alg / ms / 1e6,
-                           "fp32_tflops": flops / ms / 1e9, "share_of_step": ms / ms_per_step,
-                           "traffic": traffic.get(str(s.frame_size)) if (n_clips, args.clip_seconds) == (N_CLIPS, CLIP_SECONDS) else None})
+    full_size = (n_clips, args.clip_seconds) == (N_CLIPS, CLIP_SECONDS)
+
+    def spec_flops(s):
+        return packed.total_frames * (2.5 * s.frame_size * np.log2(s.frame_size) + s.frame_size
+                                      + 4 * s.frame_size / 2 + 2 * len(s.filterbank.banded()[3]) + 3 * s.num_bands)
+    if fe.one_launch:      # ONE kernel runs all resolutions: every input sample and every output element once
+        ms = float(np.mean([a.elapsed_time(b) for rr, a, b in launch_events]))
+        alg = in_bytes + out_bytes
+        per_kernel.append({"frame_size": "1024+2048+4096", "ms": ms, "alg_bytes": alg, "gbs": alg / ms / 1e6,
+                           "fp32_tflops": sum(spec_flops(s) for s in specs) / ms / 1e9, "share_of_step": ms / ms_per_step,
+                           "traffic": traffic.get("multi") if full_size else None})
+    else:
+        for r, s in enumerate(specs):
+            ms = float(np.mean([a.elapsed_time(b) for rr, a, b in launch_events if rr == r]))
+            alg = in_bytes + packed.total_frames * s.out_width * 4
+            per_kernel.append({"frame_size": s.frame_size, "ms": ms, "alg_bytes": alg, "gbs": alg / ms / 1e6,
+                               "fp32_tflops": spec_flops(s) / ms / 1e9, "share_of_step": ms / ms_per_step,
+                               "traffic": traffic.get(str(s.frame_size)) if full_size else None})
     dom = max(per_kernel, key=lambda k: k["ms"])
     fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
     roofline = {"bound": "hbm", "achieved": dom["gbs"], "peak": peak, "unit": "GB/s", "frac": dom["gbs"] / peak,
                 "traffic": dom["traffic"], "traffic_source": traffic.get("source"),
                 "peak_source": peak_src,
-                "kernel": ("k_front<%d>" if os.environ.get("B200SPEC_PAIR", "1")[:1] == "0" else "k_front_pair<%d>") % dom["frame_size"]
-                + " (fused frame+FFT+filterbank+log+diff" + ("" if os.environ.get("B200SPEC_PAIR", "1")[:1] == "0" else ", two frames per complex FFT") + ")",
+                "kernel": ("k_front_multi (all three resolutions in one launch" if fe.one_launch else "k_front_pair<%d> (" % dom["frame_size"])
+                + "fused frame+FFT+filterbank+log+diff, two frames per complex FFT)",
+                "launches_per_step": "1 front-end kernel + 1 task-table kernel" if fe.one_launch else "3 front-end kernels + 3 task-table kernels",
                 "kernel_ms": dom["ms"], "alg_bytes_per_launch": dom["alg_bytes"],
                 "fp32_tflops": dom["fp32_tflops"], "fp32_frac_of_74.5": dom["fp32_tflops"] / fp32_peak,
                 "note": "hop 441 makes the path FP32-issue bound (31-78 flop/B vs ridge 11); see DESIGN.md",
@@ -712,6 +724,8 @@ def main():
     ap.add_argument("--no-i16", action="store_true", help="skip the int16 end-to-end arm")
     ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configs (measured after the timed region)")
     ap.add_argument("--concurrent-streams", action="store_true", help="launch the three resolutions on three streams")
+    ap.add_argument("--one-launch", action="store_true", help="all three resolutions in one kernel launch (b200spec_logfilt_multi)")
+    ap.add_argument("--three-launches", action="store_true", help="one kernel launch per resolution (b200spec_logfilt)")
     ap.add_argument("--jobs-per-gpu", type=int, default=64, help="--config 5: jobs (of 4 stems) streamed per GPU")
     ap.add_argument("--config", type=int, default=2, choices=[2, 4, 5],
                     help="2: BASELINE configs[1] (default, the contract line); 4: configs[3] 4096 clips job-sharded; "

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define B200SPEC_ABI_VERSION 3
+#define B200SPEC_ABI_VERSION 4
 #define B200SPEC_MAX_RES 4          /* resolutions per plan (RNNBeatProcessor uses 3) */
 #define B200SPEC_MAX_DIFF_FRAMES 16 /* largest supported diff lag in frames */
 
@@ -180,6 +180,24 @@ int b200spec_spectrogram(const b200spec_plan *plan, int32_t res, const void *d_s
 int b200spec_logfilt(const b200spec_plan *plan, int32_t res, const void *d_sig, const int64_t *d_clip_off,
                      const int64_t *d_frame_off, int32_t n_clips, int64_t total_frames,
                      const b200spec_out_desc *out, void *d_workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * The same chain for SEVERAL resolutions of one hop in ONE launch -- what RNNBeatProcessor's
+ * ParallelProcessor + np.hstack does with three FramedSignalProcessor / STFT / filterbank / log / difference
+ * branches (/root/reference/backend/app/services/grid/beats.py:73-74; madmom features/beats.py): a group of
+ * threads takes a (clip, chunk of frames) task through every resolution in turn and writes all of the row's
+ * columns, so the chunk's samples leave HBM once (the later resolutions read them from L2) and there is one
+ * launch, one task list and one tail instead of n_res.  res[i] / outs[i] name the resolutions of the plan and
+ * where each writes (the np.hstack column offsets).  Frame sizes 1024 / 2048 / 4096 sharing hop_size and
+ * origin; B200SPEC_ERR_UNSUPPORTED if the tables of these resolutions do not fit one SM's shared memory
+ * together (b200spec_logfilt_multi_supported tells in advance) -- the per-resolution call always works.
+ */
+int b200spec_logfilt_multi(const b200spec_plan *plan, int32_t n_res, const int32_t *res, const void *d_sig,
+                           const int64_t *d_clip_off, const int64_t *d_frame_off, int32_t n_clips,
+                           int64_t total_frames, const b200spec_out_desc *outs, void *d_workspace,
+                           size_t workspace_bytes, void *stream);
+/* 1 if b200spec_logfilt_multi can run these resolutions of the plan in one launch, else 0 */
+int b200spec_logfilt_multi_supported(const b200spec_plan *plan, int32_t n_res, const int32_t *res);
 
 /*
  * Per-clip peak of the (down-mixed) samples: d_peak[c] = max_n |x_c[n]| in the plan's sample format

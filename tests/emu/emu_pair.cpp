@@ -21,16 +21,16 @@ double run_one(unsigned seed) {
     xb[i] = (float)rand() / RAND_MAX * 2.f - 1.f;
     w[i] = (float)(0.5 * (0.5 - 0.5 * cos(2 * PI * i / (F - 1))));   // hanning * 1/2
   }
-  std::vector<float2> tw2(256), tw3(C::TW3), wr(C::WR);
+  std::vector<float2> tw2(256), tw3(C::TW3C), wr(C::WR);   // tw3: compact form, row r = W_N^(2^r q)
   for (int k1 = 0; k1 < 16; ++k1)
     for (int n2 = 0; n2 < 16; ++n2) {
       double a = -2 * PI * (n2 * k1) / 256.0;
       tw2[k1 * 16 + n2] = make_float2((float)cos(a), (float)sin(a));
     }
   for (int q = 0; q <= 128; ++q)
-    for (int n3 = 0; n3 < C::R3; ++n3) {
-      double a = -2 * PI * ((double)n3 * q) / C::N;
-      tw3[n3 * 129 + q] = make_float2((float)cos(a), (float)sin(a));
+    for (int r = 0; r < C::LOG2R3; ++r) {
+      double a = -2 * PI * ((double)(1 << r) * q) / C::N;
+      tw3[r * 129 + q] = make_float2((float)cos(a), (float)sin(a));
     }
   for (int e = 0; e < C::WR; ++e) {
     double a = -2 * PI * e / C::WR;

@@ -579,3 +579,77 @@ def test_planless_calls_follow_the_pointer_device(b2):
         got = context_stack_device(t, 15)
         torch.cuda.synchronize(1)
     assert got.device.index == 1 and np.array_equal(got.cpu().numpy(), ref.dcp_context(x, 15))
+
+
+# ---- round 2: all resolutions in one launch (b200spec_logfilt_multi) --------------------------------------
+@pytest.mark.parametrize("dtype,channels", [("f32", 1), ("i16", 1), ("f32", 2)])
+def test_one_launch_front_end_matches_oracle_and_per_resolution_launches(b2, dtype, channels):
+    """k_front_multi: a group takes each (clip, chunk) task through 1024 / 2048 / 4096 in turn.  Same numbers as
+    the oracle and (to a few ulp) as three b200spec_logfilt launches; ragged batch with an empty clip and clips
+    shorter than a frame."""
+    import torch
+    from audio_tabs_b200.frontends import beat_specs
+    from audio_tabs_b200.plan import FrontEnd
+    from audio_tabs_b200.synth import synth_guitar
+    lens = [44100, 0, 517, 30000, 1, 88200 + 13, 4096]
+    clips = []
+    for i, n in enumerate(lens):
+        y = synth_guitar(3700 + i, max(n, 1) / 44100.0)[:n] if n else np.zeros(0, np.float32)
+        if channels == 2:
+            y = np.stack([y, np.roll(y, 5) * 0.25], axis=1) if n else np.zeros((0, 2), np.float32)
+        if dtype == "i16":
+            y = np.clip(np.round(y * 30000), -32768, 32767).astype(np.int16)
+        clips.append(np.ascontiguousarray(y))
+    specs = beat_specs(int16=(dtype == "i16"))
+    fe1 = FrontEnd(specs, device=0, dtype=dtype, channels=channels, one_launch=True)
+    fe3 = FrontEnd(specs, device=0, dtype=dtype, channels=channels, one_launch=False)
+    assert fe1.one_launch and not fe3.one_launch
+    packed = fe1.pack(clips)
+    flux1 = [torch.empty(packed.total_frames, device="cuda") for _ in specs]
+    flux3 = [torch.empty(packed.total_frames, device="cuda") for _ in specs]
+    st = torch.zeros(len(clips), dtype=torch.int32, device="cuda")
+    got1 = fe1.run_packed(packed, flux=flux1, clip_status=st).cpu().numpy()
+    got3 = fe3.run_packed(packed, flux=flux3).cpu().numpy()
+    o = 0
+    for c in clips:
+        mono = ref.remix(c, 1) if channels == 2 else c
+        if len(mono) == 0:
+            continue
+        want = ref.rnn_beat_preprocessor()(mono)
+        assert_close(got1[o:o + len(want)], want, what="one launch %s/%d" % (dtype, channels))
+        o += len(want)
+    assert o == got1.shape[0]
+    # Not bitwise: the two paths cut the clips into different (clip, chunk) tasks, so a given frame travels through
+    # the pair transform with a different partner frame, and the partner's rounding noise (1e-7 of the larger
+    # frame) leaks into it.  Both are within the oracle tolerance; against each other they agree to a few ulp.
+    np.testing.assert_allclose(got1, got3, rtol=2e-5, atol=4e-6)
+    for a, b in zip(flux1, flux3):
+        np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=2e-5, atol=2e-5)
+    assert st.cpu().tolist() == [0] * len(clips)
+
+
+def test_one_launch_onset_front_end_and_large_batch(b2):
+    """RNNOnsetProcessor's resolutions (6 / 6 / 6 bands per octave, log10(5x + 1), ratio 0.25 -> lags 1 / 2 / 3) in
+    one launch, and a batch large enough for several tasks per group."""
+    import torch
+    from audio_tabs_b200.frontends import beat_specs, onset_specs
+    from audio_tabs_b200.plan import FrontEnd
+    from audio_tabs_b200.synth import synth_guitar
+    x = synth_guitar(4242, 2.0)
+    got = FrontEnd(onset_specs(), device=0, one_launch=True).process_batch([x])[0]
+    assert_close(got, np.load(GOLD / "guitar_2s_onset266.npy"), what="one launch onset266")
+    clips = [synth_guitar(3800 + i, 6.0 + 0.37 * i) for i in range(24)]
+    a = FrontEnd(beat_specs(), device=0, one_launch=True).process_batch(clips)
+    b = FrontEnd(beat_specs(), device=0, one_launch=False).process_batch(clips)
+    for u, v in zip(a, b):
+        np.testing.assert_allclose(u, v, rtol=2e-5, atol=4e-6)
+    assert_close(a[5], ref.rnn_beat_preprocessor()(clips[5]), what="one launch, clip 5 of 24")
+
+
+def test_one_launch_rejects_what_it_cannot_run(b2):
+    from audio_tabs_b200.frontends import log_filt_spec
+    from audio_tabs_b200.plan import FrontEnd
+    with pytest.raises(ValueError):
+        FrontEnd([log_filt_spec(4096, 441.0, 12), log_filt_spec(8192, 441.0, 24, 65.0, 2100.0)], device=0, one_launch=True)
+    with pytest.raises(ValueError):
+        FrontEnd([log_filt_spec(2048, 441.0, 12)], device=0, one_launch=True)       # a single resolution: nothing to fuse

@@ -81,6 +81,40 @@ def test_mel_db_matches_oracle(cuda_device):
 
 
 @pytest.mark.gpu
+def test_mel_db_error_is_the_float32_fft_floor(cuda_device):
+    """Why the dB tolerances of this file are looser than the 1e-4 of the madmom path: the
+    oracle transforms in float64, and ANY float32 FFT leaves a noise floor of ~1e-7 of the frame's energy in
+    every bin; in a mel band 60-80 dB below the clip's maximum that floor is a visible fraction of the band, and
+    10 log10 turns it into 1e-2 dB.  Shown with a yardstick that shares no code with the kernel: the same
+    spectrogram through a float32 cuFFT (torch.fft, test-only) misses the float64 oracle by as much as we do."""
+    import torch
+    from audio_tabs_b200.onsets import OnsetStrength, hann_periodic
+    from audio_tabs_b200.synth import synth_guitar
+    y = synth_guitar(4100, 3.0)
+    eng = OnsetStrength(sr=SR)
+    ours = eng.mel_db(eng.fe.pack([y])).cpu().numpy().astype(np.float64)
+    want = lr.power_to_db(lr.melspectrogram(y, sr=SR), top_db=None).astype(np.float64)
+    # yardstick: float32 frames x float32 periodic Hann -> cuFFT float32 -> |X|^2 -> the oracle's mel basis -> dB
+    yp = torch.from_numpy(np.pad(y, 1024)).cuda()
+    frames = yp.unfold(0, 2048, 512) * torch.from_numpy(hann_periodic(2048).astype(np.float32)).cuda()
+    S32 = (torch.fft.rfft(frames, dim=1).abs() ** 2).cpu().numpy()
+    basis = lr.mel(sr=SR, n_fft=2048)
+    yard = lr.power_to_db(np.einsum("tf,mf->tm", S32, basis).astype(np.float32), top_db=None).astype(np.float64)
+    assert yard.shape == want.shape == ours.shape
+    top = want.max()
+    for lo, hi in ((-40.0, 0.0), (-60.0, -40.0), (-80.0, -60.0)):                 # dB below the clip maximum
+        sel = (want > top + lo) & (want <= top + hi)
+        if sel.sum() < 50:
+            continue
+        e_ours, e_yard = np.abs(ours - want)[sel], np.abs(yard - want)[sel]
+        # the same order of magnitude as another float32 FFT, at the maximum and at the 99th percentile
+        assert e_ours.max() <= 4.0 * e_yard.max() + 1e-4, (lo, hi, e_ours.max(), e_yard.max())
+        assert np.percentile(e_ours, 99) <= 4.0 * np.percentile(e_yard, 99) + 1e-4, (lo, hi)
+    loud = want > top - 40.0
+    assert np.abs(ours - want)[loud].max() < 1e-3                                  # float32-tight where it can be
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("aggregate", [None, np.median])
 def test_onset_strength_matches_oracle(cuda_device, aggregate):
     from audio_tabs_b200 import onsets
