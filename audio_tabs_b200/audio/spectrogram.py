@@ -128,13 +128,21 @@ class FilteredSpectrogramProcessor(Processor):
         return out
 
 
+# log functions the device evaluates: out = scale * log10(mul * x + add + shift)
+_LOG_FORMS = {np.log10: (1.0, 0.0), np.log: (float(np.log(10.0)), 0.0), np.log2: (float(1.0 / np.log10(2.0)), 0.0),
+              np.log1p: (float(np.log(10.0)), 1.0)}
+
+
 class LogarithmicSpectrogram(_Stage):
-    """log10(mul * spec + add) (madmom LogarithmicSpectrogram); only np.log10 runs on the device."""
+    """log(mul * spec + add) (madmom LogarithmicSpectrogram); log is np.log10 (madmom's default), np.log,
+    np.log2 or np.log1p -- all evaluated on the device as a scaled log10."""
 
     def __init__(self, spectrogram, log=LOG, mul=MUL, add=ADD, **kwargs):
         spectrogram = _as_spectrogram(spectrogram, **kwargs)
-        if log is not np.log10:
-            raise ValueError("only log=np.log10 is implemented on the device (madmom's default)")
+        if log not in _LOG_FORMS:
+            raise ValueError("log must be np.log10, np.log, np.log2 or np.log1p on the device (got %r)" % (log,))
+        self.log = log
+        self.log_scale, self.log_shift = _LOG_FORMS[log]
         self.source = spectrogram
         self.stft = spectrogram.stft
         self.filterbank = getattr(spectrogram, "filterbank", None)

@@ -18,6 +18,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "fb_core.cuh"
 #include "fft_core.cuh"
 
@@ -274,7 +276,11 @@ __device__ __forceinline__ int front_tail(const FrontParams &p, const TailCtx &c
     for (int t = 0; t < TBF; ++t) fluxacc[t] = 0.f;
     const int nvalid = min(TBF, f1 - fh);        // frames of this sub-batch that exist
     const int nskip = max(0, f0 - fh);           // leading warm-up frames: they only feed the difference ring
+    // the common case: every frame of the sub-batch exists, none is a warm-up row and none is among the first kd
+    // rows of the clip -- the per-frame tests below then fold away
+    const bool full = (nvalid == TBF) && (nskip == 0) && (fh >= kd);
     for (int jb = 0; jb < B; jb += kGroupThreads) {
+      if (jb + (tid & ~31) >= B) continue;       // no band for any lane of this warp (warp-uniform): nothing to do
       const int j = jb + tid;
       const bool valid = j < B;
       const int4 bd = valid ? s_band[j] : make_int4(0, 0, 0, 0);
@@ -318,36 +324,41 @@ __device__ __forceinline__ int front_tail(const FrontParams &p, const TailCtx &c
         float *pd = c.out_diff + (row0 + fh) * p.ld_out + j;
         float *hp = s_hist + hslot * B + j;
         int slot = hslot;
+        auto rows = [&](auto full_tag) {
+          constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll
-        for (int t = 0; t < TBF; ++t) {
-          if (t < nvalid) {
-            float L = ysum[t] * cscale;
-            if (c.do_log) {
-              float a = __fadd_rn(__fmul_rn(c.lmul, L), c.ladd);    // separate multiply and add, as numpy
-              if (c.lfloor > 0.f) a = fmaxf(a, c.lfloor);
-              L = fast_lg2(a) * c.lk;                               // log_scale * log10(a)
+          for (int t = 0; t < TBF; ++t) {
+            if (FULL || t < nvalid) {
+              float L = ysum[t] * cscale;
+              if (c.do_log) {
+                float a = __fadd_rn(__fmul_rn(c.lmul, L), c.ladd);    // separate multiply and add, as numpy
+                if (c.lfloor > 0.f) a = fmaxf(a, c.lfloor);
+                L = fast_lg2(a) * c.lk;                               // log_scale * log10(a)
+              }
+              nonfinite |= !(fabsf(L) <= 3.402823466e38f);           // NaN or Inf (from NaN / Inf samples)
+              float D = 0.f;
+              if (kd > 0) {
+                const float old = *hp;
+                *hp = L;
+                if (FULL || fh + t >= kd) D = L - old;
+                if (c.positive) D = fmaxf(D, 0.f);
+                ++slot;
+                hp += B;
+                if (slot == kd) slot = 0, hp -= kd * B;
+              }
+              if (p.num_classes > 0) s_lrow[t * B + j] = L;
+              if (FULL || t >= nskip) {
+                if (c.out_spec != nullptr) *ps = L;
+                if (c.out_diff != nullptr) *pd = D;
+                fluxacc[t] += D;
+              }
             }
-            nonfinite |= !(fabsf(L) <= 3.402823466e38f);           // NaN or Inf (from NaN / Inf samples)
-            float D = 0.f;
-            if (kd > 0) {
-              const float old = *hp;
-              *hp = L;
-              if (fh + t >= kd) D = L - old;
-              if (c.positive) D = fmaxf(D, 0.f);
-              ++slot;
-              hp += B;
-              if (slot == kd) slot = 0, hp -= kd * B;
-            }
-            if (p.num_classes > 0) s_lrow[t * B + j] = L;
-            if (t >= nskip) {
-              if (c.out_spec != nullptr) *ps = L;
-              if (c.out_diff != nullptr) *pd = D;
-              fluxacc[t] += D;
-            }
+            ps += p.ld_out;
+            pd += p.ld_out;
           }
-          ps += p.ld_out;
-          pd += p.ld_out;
-        }
+        };
+        if (full) rows(std::true_type{});
+        else rows(std::false_type{});
       }
     }
     if (kd > 0) {                                // ring position of the next step's first frame

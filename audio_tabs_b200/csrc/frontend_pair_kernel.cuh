@@ -386,24 +386,37 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front_multi(const Multi
 #pragma unroll
   for (int n2 = 0; n2 < 16; ++n2) tw2r[n2] = __ldg(&p0.tw2[(tid & 15) * 16 + n2]);
   const int total_tasks = p0.task_off[p0.n_clips];
+  (void)s_task;
 
+  // The G groups of a CTA take G consecutive tasks and walk through the resolutions IN STEP (a CTA barrier per
+  // resolution): all warps of the SM then run the same code at the same time -- the three resolutions' unrolled
+  // FFT bodies are 370 KB of SASS, and groups in different resolutions evict each other's instructions -- and
+  // neighbouring chunks of one clip share their boundary samples in L1.  The groups do the same amount of work
+  // per resolution, so the barrier costs little.
+  __shared__ int s_base;
   for (;;) {
-    if (tid == 0) *s_task = atomicAdd(p0.task_counter, 1);
-    group_bar(g);
-    const int task = *s_task;
-    group_bar(g);
-    if (task >= total_tasks) break;
-    const int c = task_clip(p0.task_off, p0.n_clips, task);
-    const int T = (int)(p0.frame_off[c + 1] - p0.frame_off[c]);
-    const int f0 = (task - p0.task_off[c]) * p0.chunk;
-    const int f1 = min(T, f0 + p0.chunk);
+    if (threadIdx.x == 0) s_base = atomicAdd(p0.task_counter, G);
+    __syncthreads();
+    const int base = s_base;
+    if (base >= total_tasks) break;
+    const int task = base + g;
+    const bool valid = task < total_tasks;
+    int c = 0, f0 = 0, f1 = 0;
+    if (valid) {
+      c = task_clip(p0.task_off, p0.n_clips, task);
+      const int T = (int)(p0.frame_off[c + 1] - p0.frame_off[c]);
+      f0 = (task - p0.task_off[c]) * p0.chunk;
+      f1 = min(T, f0 + p0.chunk);
+    }
 #pragma unroll 1
     for (int i = 0; i < m.n_res; ++i) {
       const FrontParams &p = m.r[i];
-      if (p.frame_size == 1024) pair_run_task<typename MultiCfg<1024>::type, 1024, IN, true>(p, smem, gmem, g, tid, tw2r, c, f0, f1);
-      else if (p.frame_size == 2048) pair_run_task<typename MultiCfg<2048>::type, 2048, IN, true>(p, smem, gmem, g, tid, tw2r, c, f0, f1);
-      else pair_run_task<typename MultiCfg<4096>::type, 4096, IN, true>(p, smem, gmem, g, tid, tw2r, c, f0, f1);
-      group_bar(g);      // the band stage of this resolution has read its buffers before the next one reuses them
+      if (valid) {
+        if (p.frame_size == 1024) pair_run_task<typename MultiCfg<1024>::type, 1024, IN, true>(p, smem, gmem, g, tid, tw2r, c, f0, f1);
+        else if (p.frame_size == 2048) pair_run_task<typename MultiCfg<2048>::type, 2048, IN, true>(p, smem, gmem, g, tid, tw2r, c, f0, f1);
+        else pair_run_task<typename MultiCfg<4096>::type, 4096, IN, true>(p, smem, gmem, g, tid, tw2r, c, f0, f1);
+      }
+      __syncthreads();   // every group is done with this resolution (and its buffers) before any starts the next
     }
   }
 }

@@ -50,7 +50,7 @@ def _parse(stage):
                                     SpectrogramDifference, StackedDifference)
     from .audio.stft import ShortTimeFourierTransform
     from .audio.chroma import FoldedChroma
-    rec = dict(stack=False, diff=None, log=None, filterbank=None, magnitude=False, stft=None, host=None,
+    rec = dict(stack=False, diff=None, log=None, log_scale=1.0, filterbank=None, magnitude=False, stft=None, host=None,
                fold=None)
     node = stage
     if isinstance(node, FoldedChroma):
@@ -63,7 +63,8 @@ def _parse(stage):
         rec["diff"] = (node.diff_frames, bool(node.positive_diffs), int(node.diff_max_bins or 0))
         node = node.source
     if isinstance(node, LogarithmicSpectrogram):
-        rec["log"] = (float(node.mul), float(node.add))
+        rec["log"] = (float(node.mul), float(node.add) + float(getattr(node, "log_shift", 0.0)))
+        rec["log_scale"] = float(getattr(node, "log_scale", 1.0))
         node = node.source
     if isinstance(node, FilteredSpectrogram):
         rec["filterbank"] = node.filterbank
@@ -88,9 +89,11 @@ def _spec_from(rec, stft=None, frame_size=None):
         return ResolutionSpec(frame_size=stft.frames.frame_size, hop_size=stft.frames.hop_size,
                               origin=stft.frames.origin, fft_window=np.asarray(stft.fft_window),
                               filterbank=rec["filterbank"], log=rec["log"] is not None, mul=mul, add=add,
-                              diff_frames=diff_frames, positive_diffs=positive, diff_max_bins=max_bins, **fold)
+                              log_scale=rec["log_scale"], diff_frames=diff_frames, positive_diffs=positive,
+                              diff_max_bins=max_bins, **fold)
     return ResolutionSpec(frame_size=frame_size, filterbank=rec["filterbank"], log=rec["log"] is not None,
-                          mul=mul, add=add, diff_frames=diff_frames, positive_diffs=positive, diff_max_bins=max_bins)
+                          mul=mul, add=add, log_scale=rec["log_scale"], diff_frames=diff_frames, positive_diffs=positive,
+                          diff_max_bins=max_bins)
 
 
 def _frame_off(total, device):

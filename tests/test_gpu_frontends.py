@@ -653,3 +653,41 @@ def test_one_launch_rejects_what_it_cannot_run(b2):
         FrontEnd([log_filt_spec(4096, 441.0, 12), log_filt_spec(8192, 441.0, 24, 65.0, 2100.0)], device=0, one_launch=True)
     with pytest.raises(ValueError):
         FrontEnd([log_filt_spec(2048, 441.0, 12)], device=0, one_launch=True)       # a single resolution: nothing to fuse
+
+
+# ---- round 2: remaining madmom options -------------------------------------------------------------------
+@pytest.mark.parametrize("log", [np.log, np.log2, np.log1p])
+def test_other_log_functions(b2, log):
+    """LogarithmicSpectrogramProcessor(log=np.log / np.log2 / np.log1p): evaluated on the device as a scaled log10"""
+    from audio_tabs_b200.synth import synth_guitar
+    x = synth_guitar(3900, 1.0)
+
+    def chain(m, lg):
+        return m.SequentialProcessor((
+            m.SignalProcessor(num_channels=1, sample_rate=SR), m.FramedSignalProcessor(frame_size=2048, fps=100),
+            m.ShortTimeFourierTransformProcessor(), m.FilteredSpectrogramProcessor(num_bands=12),
+            m.LogarithmicSpectrogramProcessor(log=lg, mul=2.0, add=1.0)))
+    want = chain(ref, log)(x).data
+    got = np.asarray(chain(b2, log)(x))
+    assert_close(got, want, what="log=%s" % log.__name__)
+    with pytest.raises(ValueError):
+        chain(b2, np.sqrt)(x)
+    # the stand-alone stage (host spectrogram in) takes the same functions
+    mag = np.abs(ref.ShortTimeFourierTransform(ref.FramedSignal(ref.Signal(x, sample_rate=SR), frame_size=2048)).data)
+    got2 = np.asarray(b2.LogarithmicSpectrogram(b2.Spectrogram(mag), log=log, mul=2.0, add=1.0))
+    assert_close(got2, log(np.float32(2.0) * mag + np.float32(1.0)).astype(np.float32), what="stand-alone log=%s" % log.__name__)
+
+
+def test_fused_multi_resolution_front_end_honours_norm(b2):
+    """rnn_beat_frontend_fused() on a DeviceSignal with norm=True applies the per-clip gain, like the
+    per-branch chain does"""
+    import torch
+    from audio_tabs_b200.audio.signal import SignalProcessor
+    from audio_tabs_b200.frontends import MultiResolutionFrontEnd, beat_specs
+    from audio_tabs_b200.synth import synth_guitar
+    x = synth_guitar(3901, 1.5) * 0.17
+    sig = SignalProcessor(num_channels=1, sample_rate=SR, norm=True)(torch.from_numpy(x).cuda())
+    got = MultiResolutionFrontEnd(beat_specs())(sig)
+    assert_close(got, ref.rnn_beat_preprocessor()(x / np.abs(x).max()), what="fused front end, norm=True")
+    with pytest.raises(NotImplementedError):
+        SignalProcessor(num_channels=1, sample_rate=SR, gain=6.0)(torch.from_numpy(x).cuda())
