@@ -9,7 +9,7 @@ import ctypes as C
 import os
 from pathlib import Path
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_RES = 4
 MAX_DIFF_FRAMES = 16
 
@@ -47,6 +47,7 @@ class ResDesc(C.Structure):
         ("power", C.c_int32),
         ("log_scale", C.c_float),
         ("log_floor", C.c_float),
+        ("circular_shift", C.c_int32),
     ]
 
 

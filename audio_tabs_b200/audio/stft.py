@@ -53,21 +53,36 @@ class ShortTimeFourierTransform(LazyArray):
             window = window(frame_size)
         if fft_window is None:
             fft_window = np.ones(frame_size)               # window=None: rectangular
-        if fft_size is not None and int(fft_size) != frame_size:
-            raise ValueError("fft_size != frame_size is not supported by the CUDA path")
-        if circular_shift:
-            raise ValueError("circular_shift=True is not supported by the CUDA path")
+        fft_size = frame_size if fft_size is None else int(fft_size)
+        if fft_size not in (1024, 2048, 4096, 8192):
+            raise ValueError("the CUDA path transforms 1024, 2048, 4096 or 8192 points (fft_size %d); give one of them "
+                             "as fft_size for another frame_size" % fft_size)
+        if circular_shift and fft_size != frame_size:
+            raise ValueError("circular_shift=True with fft_size != frame_size is not supported by the CUDA path")
         if include_nyquist:
             raise ValueError("include_nyquist=True is not supported by the CUDA path")
         self.frames = frames
         self.window = window
         self.fft_window = fft_window
-        self.fft_size = frame_size
-        self.circular_shift = circular_shift
+        self.fft_size = fft_size
+        self.circular_shift = bool(circular_shift)
         self.include_nyquist = include_nyquist
         self.fftw = None
-        self.bin_frequencies = fft_frequencies(frame_size >> 1, frames.signal.sample_rate) \
-            if frames.signal.sample_rate else np.arange(frame_size >> 1, dtype=float)
+        self.bin_frequencies = fft_frequencies(fft_size >> 1, frames.signal.sample_rate) \
+            if frames.signal.sample_rate else np.arange(fft_size >> 1, dtype=float)
+
+    def kernel_window_and_origin(self):
+        """(window of fft_size points, origin) that make the kernel's frame [int(n hop) - fft_size/2 - origin, + fft_size)
+        start where madmom's frame starts: scipy.fftpack.fft(frame * window, fft_size) zero-pads (or cuts) the windowed
+        frame at its END, so the window is padded / cut the same way and the origin absorbs the difference of the two
+        half lengths."""
+        win = np.asarray(self.fft_window, dtype=np.float64)
+        frame_size = self.frames.frame_size
+        if self.fft_size > frame_size:
+            win = np.concatenate((win, np.zeros(self.fft_size - frame_size)))
+        elif self.fft_size < frame_size:
+            win = win[:self.fft_size]
+        return win, self.frames.origin + frame_size // 2 - self.fft_size // 2
 
     def _result_shape(self):
         return (self.frames.num_frames, self.fft_size >> 1)

@@ -85,6 +85,8 @@ struct FrontParams {
   // outputs (MODE_SPECTRUM)
   float *spec_out;      // (rows, N) float or float2
   int spec_complex;
+  int circular_shift;   // madmom stft(circular_shift=True) with fft_size == frame_size: the two halves of the windowed
+                        // frame are swapped before the transform = bin k times (-1)^k (magnitudes are unchanged)
   // shared-memory carve-up (byte offsets), filled by front_smem_layout()
   int o_win, o_tw3, o_pt, o_wr, o_w4, o_band, o_dw, o_proj, o_groups, group_bytes;
   int g_mags, g_partial, g_hist, g_lrow, g_red, g_task;  // offsets inside a group's block
@@ -574,11 +576,11 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
               float2 *o = reinterpret_cast<float2 *>(p.spec_out) + row * N;
               if (u != 0)
                 fft_pass3_unit<F>(u, fbuf + pa_off, fbuf + pb_off, s_tw3 + u, s_pt + u,
-                                  [&](int k, float2 X) { o[k] = X; });
+                                  [&](int k, float2 X) { o[k] = (p.circular_shift && (k & 1)) ? make_float2(-X.x, -X.y) : X; });
               if (tid < 2 * R3) {
                 int bin;
                 const float2 X = fft_pass3_selfpaired<F>(tid, fbuf, s_wr, s_pt, bin);
-                o[bin] = X;
+                o[bin] = (p.circular_shift && (bin & 1)) ? make_float2(-X.x, -X.y) : X;
               }
             } else {
               float *o = p.spec_out + row * N;

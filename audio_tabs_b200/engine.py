@@ -86,8 +86,9 @@ def _spec_from(rec, stft=None, frame_size=None):
     mul, add = rec["log"] if rec["log"] else (1.0, 1.0)
     fold = dict(proj_classes=rec["fold"][0], num_classes=rec["fold"][1]) if rec.get("fold") else {}
     if stft is not None:
-        return ResolutionSpec(frame_size=stft.frames.frame_size, hop_size=stft.frames.hop_size,
-                              origin=stft.frames.origin, fft_window=np.asarray(stft.fft_window),
+        win, origin = stft.kernel_window_and_origin()
+        return ResolutionSpec(frame_size=stft.fft_size, hop_size=stft.frames.hop_size,
+                              origin=origin, fft_window=win, circular_shift=stft.circular_shift,
                               filterbank=rec["filterbank"], log=rec["log"] is not None, mul=mul, add=add,
                               log_scale=rec["log_scale"], diff_frames=diff_frames, positive_diffs=positive,
                               diff_max_bins=max_bins, **fold)

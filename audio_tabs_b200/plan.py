@@ -55,6 +55,7 @@ class ResolutionSpec:
     power: bool = False                         # filterbank on |X|^2 (librosa melspectrogram) instead of |X|
     log_scale: float = 1.0                      # out = log_scale * log10(max(mul*y + add, log_floor))
     log_floor: float = 0.0                      # <= 0: no clamp (madmom); librosa power_to_db: amin = 1e-10
+    circular_shift: bool = False                # STFT of the half-swapped frame: bin k times (-1)^k (complex output only)
     proj_classes: Optional[np.ndarray] = None   # per band class index (or -1), e.g. chroma fold
     proj_matrix: Optional[np.ndarray] = None    # or a dense (B, C) projection
     num_classes: int = 0
@@ -100,7 +101,8 @@ class ResolutionSpec:
             _digest(None if self.filterbank is None else np.asarray(self.filterbank)),
             int(self.log), repr(float(self.mul)), repr(float(self.add)), self.diff_frames,
             int(self.positive_diffs), int(self.diff_max_bins or 0), int(bool(self.power)),
-            repr(float(self.log_scale)), repr(float(self.log_floor)), _digest(self.proj_off, self.proj_band, self.proj_weight))))
+            repr(float(self.log_scale)), repr(float(self.log_floor)), int(bool(self.circular_shift)),
+            _digest(self.proj_off, self.proj_band, self.proj_weight))))
 
     @property
     def num_bins(self):
@@ -150,6 +152,7 @@ class DevicePlan:
             r.diff_frames, r.positive_diffs = int(s.diff_frames), int(bool(s.positive_diffs))
             r.diff_max_bins = int(s.diff_max_bins or 0)
             r.power, r.log_scale, r.log_floor = int(bool(s.power)), float(s.log_scale), float(s.log_floor)
+            r.circular_shift = int(bool(s.circular_shift))
             r.num_classes = int(s.num_classes) if s.proj_off is not None else 0
             if s.proj_off is not None:
                 r.proj_off, r.proj_band, r.proj_weight = iptr(s.proj_off), iptr(s.proj_band), fptr(s.proj_weight)

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define B200SPEC_ABI_VERSION 4
+#define B200SPEC_ABI_VERSION 5
 #define B200SPEC_MAX_RES 4          /* resolutions per plan (RNNBeatProcessor uses 3) */
 #define B200SPEC_MAX_DIFF_FRAMES 16 /* largest supported diff lag in frames */
 
@@ -70,7 +70,10 @@ typedef enum b200spec_end_mode {
  *  madmom/audio/filters.py and passes the float32 weights through unchanged.)
  */
 typedef struct b200spec_res_desc {
-  int32_t frame_size;        /* 1024, 2048, 4096 or 8192 (fft_size == frame_size, no Nyquist bin) */
+  int32_t frame_size;        /* FFT length: 1024, 2048, 4096 or 8192 (no Nyquist bin).  A madmom frame_size != fft_size is
+                              * expressed by the caller: window zero-padded (or cut) to the FFT length and
+                              * origin += frame_size / 2 - fft_size / 2, so that samples [int(n*hop) - fft/2 - origin, + fft)
+                              * start where madmom's frame starts */
   double hop_size;           /* samples, may be fractional (sample_rate / fps) */
   int32_t origin;            /* integer origin as resolved by FramedSignal (0 for 'center') */
   const float *window;       /* host, frame_size floats: madmom's fft_window rounded to float32 */
@@ -103,6 +106,9 @@ typedef struct b200spec_res_desc {
   int32_t power;
   float log_scale;
   float log_floor;
+  /* madmom stft(circular_shift=True) with fft_size == frame_size: the halves of the windowed frame are swapped before
+   * the transform, i.e. bin k of b200spec_stft's output is multiplied by (-1)^k.  Magnitude outputs do not change. */
+  int32_t circular_shift;
 } b200spec_res_desc;
 
 typedef struct b200spec_plan_desc {

@@ -691,3 +691,108 @@ def test_fused_multi_resolution_front_end_honours_norm(b2):
     assert_close(got, ref.rnn_beat_preprocessor()(x / np.abs(x).max()), what="fused front end, norm=True")
     with pytest.raises(NotImplementedError):
         SignalProcessor(num_channels=1, sample_rate=SR, gain=6.0)(torch.from_numpy(x).cuda())
+
+
+@pytest.mark.parametrize("frame_size,fft_size", [(2048, 4096), (3000, 4096), (2048, 1024), (1500, 2048), (6000, 8192)])
+def test_fft_size_different_from_frame_size(b2, frame_size, fft_size):
+    """madmom stft(fft_size=...): the windowed frame is zero-padded (or cut) at its end to fft_size points; any
+    frame_size works as long as fft_size is one of the transform lengths"""
+    from audio_tabs_b200.synth import synth_guitar
+    x = synth_guitar(3950 + fft_size, 0.8)
+
+    def stft_of(m):
+        frames = m.FramedSignal(m.Signal(x, sample_rate=SR), frame_size=frame_size, hop_size=441.0)
+        return m.ShortTimeFourierTransform(frames, fft_size=fft_size)
+    want = stft_of(ref)
+    got = stft_of(b2)
+    assert got.shape == want.data.shape == (80, fft_size // 2)
+    assert np.array_equal(got.bin_frequencies, want.bin_frequencies)
+    assert_stft_close(np.asarray(got), want.data)
+
+    def chain(m):
+        return m.SequentialProcessor((
+            m.SignalProcessor(num_channels=1, sample_rate=SR), m.FramedSignalProcessor(frame_size=frame_size, fps=100),
+            m.ShortTimeFourierTransformProcessor(fft_size=fft_size), m.FilteredSpectrogramProcessor(num_bands=12),
+            m.LogarithmicSpectrogramProcessor(mul=1, add=1),
+            m.SpectrogramDifferenceProcessor(diff_ratio=0.5, positive_diffs=True, stack_diffs=np.hstack)))
+    assert_close(np.asarray(chain(b2)(x)), chain(ref)(x), what="log-filtered chain, frame %d fft %d" % (frame_size, fft_size))
+    with pytest.raises(ValueError):
+        b2.ShortTimeFourierTransform(b2.FramedSignal(b2.Signal(x, sample_rate=SR), frame_size=frame_size), fft_size=3000)
+
+
+@pytest.mark.parametrize("frame_size", [1024, 2048, 8192])
+def test_circular_shift(b2, frame_size):
+    """madmom stft(circular_shift=True): the halves of the windowed frame are swapped = bin k times (-1)^k"""
+    from audio_tabs_b200.synth import synth_guitar
+    x = synth_guitar(3960 + frame_size, 0.7)
+
+    def stft_of(m, **kw):
+        return m.ShortTimeFourierTransform(m.FramedSignal(m.Signal(x, sample_rate=SR), frame_size=frame_size), **kw)
+    want = stft_of(ref, circular_shift=True).data
+    got = np.asarray(stft_of(b2, circular_shift=True))
+    assert_stft_close(got, want)
+    plain = np.asarray(stft_of(b2))
+    assert np.array_equal(got[:, 0::2], plain[:, 0::2]) and np.array_equal(got[:, 1::2], -plain[:, 1::2])
+    # magnitudes, and everything downstream of them, do not change
+    spec = np.asarray(b2.Spectrogram(stft_of(b2, circular_shift=True)))
+    assert_close(spec, np.abs(want), rtol=1e-4, atol=1e-4 * np.abs(want).max(), what="spectrogram of the shifted STFT")
+    with pytest.raises(ValueError):
+        b2.ShortTimeFourierTransform(b2.FramedSignal(b2.Signal(x, sample_rate=SR), frame_size=1000), fft_size=1024,
+                                     circular_shift=True)
+
+
+@pytest.mark.parametrize("seed", list(range(24)))
+def test_randomized_configurations(b2, seed):
+    """Seeded random configurations of the fused chain -- frame size, (fractional) hop, origin, bands per octave,
+    frequency range, mul / add, difference lag, sample format, channel count, ragged clip lengths down to one
+    sample -- against the oracle: the cases nobody thought of writing down."""
+    from audio_tabs_b200.frontends import log_filt_spec
+    from audio_tabs_b200.plan import FrontEnd
+    from audio_tabs_b200.synth import synth_guitar
+    rng = np.random.default_rng(9000 + seed)
+    frame_size = int(rng.choice([1024, 2048, 4096, 8192]))
+    hop = float(rng.choice([441.0, 512.0, 4410.0, 8820.0, SR / 7.0, float(rng.integers(64, 6000)) + float(rng.choice([0.0, 0.5, 0.25]))]))
+    bpo = int(rng.choice([3, 6, 12, 24]))
+    fmin = float(rng.choice([30.0, 65.0, 100.0, 27.5]))
+    fmax = float(rng.choice([17000.0, 2100.0, 8000.0, 16000.0]))
+    mul, add = float(rng.choice([1.0, 5.0, 0.5])), float(rng.choice([1.0, 0.5, 2.0]))
+    ratio = rng.choice([None, 0.5, 0.25])
+    dtype = str(rng.choice(["f32", "i16"]))
+    channels = int(rng.choice([1, 1, 2]))
+    origin = int(rng.choice([0, 0, 0, (frame_size - 1) // 2, -(frame_size // 2)]))      # 'center', 'online', 'stream'
+    try:
+        spec = log_filt_spec(frame_size, hop, bpo, fmin, fmax, mul=mul, add=add, diff_ratio=None if ratio is None else float(ratio),
+                             int16=(dtype == "i16"), origin=origin)
+    except ValueError:
+        pytest.skip("filterbank not constructible for this draw")
+    lens = [int(v) for v in rng.choice([1, 7, 300, frame_size - 1, frame_size, 3 * frame_size + 17, 40000, 66150], size=5)]
+    clips = []
+    for i, n in enumerate(lens):
+        y = synth_guitar(9100 + 10 * seed + i, max(n, 64) / SR)[:n]
+        if channels == 2:
+            y = np.stack([y, np.roll(y, 3) * 0.5], axis=1)
+        if dtype == "i16":
+            y = np.clip(np.round(y * 28000), -32768, 32767).astype(np.int16)
+        clips.append(np.ascontiguousarray(y))
+    fe = FrontEnd([spec], device=0, dtype=dtype, channels=channels)
+    got = fe.process_batch(clips)
+    for c, g in zip(clips, got):
+        mono = ref.remix(c, 1) if channels == 2 else c
+        chain = [ref.SignalProcessor(num_channels=1, sample_rate=SR),
+                 ref.FramedSignalProcessor(frame_size=frame_size, hop_size=hop, origin=origin),
+                 ref.ShortTimeFourierTransformProcessor(),
+                 ref.FilteredSpectrogramProcessor(num_bands=bpo, fmin=fmin, fmax=fmax),
+                 ref.LogarithmicSpectrogramProcessor(mul=mul, add=add)]
+        if ratio is not None:
+            chain.append(ref.SpectrogramDifferenceProcessor(diff_ratio=float(ratio), positive_diffs=True, stack_diffs=np.hstack))
+        want = ref.SequentialProcessor(chain)(mono)
+        want = np.asarray(want.data if hasattr(want, "data") and not isinstance(want, np.ndarray) else want).astype(np.float32)
+        what = "seed %d: frame %d hop %r bpo %d %s/%d origin %d diff %s" % (seed, frame_size, hop, bpo, dtype, channels, origin, ratio)
+        if ratio is None:
+            assert_close(g, want, what=what)
+        else:
+            # [spec | diff]: a difference of two log values carries the absolute error of both (near 0 the relative
+            # term gives no room), so its absolute tolerance is twice that of a value
+            B = want.shape[1] // 2
+            assert_close(g[:, :B], want[:, :B], what=what + " (spec)")
+            assert_close(g[:, B:], want[:, B:], atol=2e-5, what=what + " (diff)")
