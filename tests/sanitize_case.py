@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Smallest run that touches every kernel family (for compute-sanitizer): the beat front end (pair kernels
 1024/2048/4096 + diff), a ragged batch, the 8192 chain (k_front, pruned magnitudes), stereo int16 input,
-chroma projection, SuperFlux, onset strength, context stacking.  Results are checked against the oracle."""
+the one-launch kernel, chroma projection, SuperFlux, onset strength, context stacking.  Results are checked against the oracle."""
 import sys
 from pathlib import Path
 import numpy as np
@@ -21,6 +21,9 @@ x = synth_guitar(1, 0.6)
 fe = FrontEnd(beat_specs(), device=0)
 outs = fe.process_batch([x, x[:5000], x[:300]])
 ok = close(outs[0], ref.rnn_beat_preprocessor()(x)) and close(outs[2], ref.rnn_beat_preprocessor()(x[:300]))
+one = FrontEnd(beat_specs(), device=0, one_launch=True)        # k_front_multi: all resolutions in one launch, with status
+outs1, status = one.process_batch([x, x[:5000], x[:300]], return_status=True)
+ok &= close(outs1[0], ref.rnn_beat_preprocessor()(x)) and close(outs1[1], ref.rnn_beat_preprocessor()(x[:5000])) and not status.any()
 st = np.stack([x, x * 0.5], axis=1)
 i16 = np.clip(np.round(st * 20000), -32768, 32767).astype(np.int16)
 o16 = FrontEnd(beat_specs(int16=True), device=0, dtype="i16", channels=2).process_batch([i16])[0]

@@ -168,12 +168,12 @@ def test_cnn_key_processor_after_install(stub, cuda_device, tmp_path):
 
 
 def test_madmom_golden_script_against_the_stub(stub, monkeypatch, capsys):
-    """tools/make_madmom_golden.py (the script that pins the oracle wherever the real madmom exists) runs end to
+    """tests/golden/make_madmom_golden.py (the script that pins the oracle wherever the real madmom exists) runs end to
     end: against the stub -- whose numerics are the oracle's -- every comparison must pass, including the
     committed fixtures under tests/golden/."""
     import importlib.util
     from pathlib import Path
-    path = Path(__file__).resolve().parents[1] / "tools" / "make_madmom_golden.py"
+    path = Path(__file__).resolve().parent / "golden" / "make_madmom_golden.py"
     spec = importlib.util.spec_from_file_location("make_madmom_golden", path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
