@@ -10,7 +10,10 @@ What it restates and why: the reference calls ``librosa.onset.onset_strength(y=y
 ``librosa==0.10.2.post1`` (/root/reference/backend/requirements.txt:14), is NOT vendored under
 /root/reference and is not installed here (no network), so -- exactly as for madmom -- this is a
 restatement of its published algorithm and **parity is unpinned**: no golden vector of the reference
-covers this path.  Functions cite the librosa function they follow:
+covers this path.  (Partial external pin, round 2: the mel filterbank, the power mel spectrogram in dB and the
+top_db clip agree with ``transformers.audio_utils``, a third-party numpy port of the same librosa functions
+that is installed in this image -- tests/test_oracle_crosscheck.py; ``onset_strength`` itself has no such
+counterpart.)  Functions cite the librosa function they follow:
 
   librosa.core.convert.{hz_to_mel, mel_to_hz, mel_frequencies, fft_frequencies}
   librosa.filters.mel                       (Slaney scale, norm='slaney', float32)

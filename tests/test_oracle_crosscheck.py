@@ -169,3 +169,34 @@ def test_committed_goldens_against_the_second_statement():
                                rtol=2e-6, atol=2e-6)
     np.testing.assert_allclose(np.load(gold / "refjob_3s_key105.npy"), front_end64(clip, 8192, 8820.0, 24, 65, 2100),
                                rtol=2e-6, atol=2e-6)
+
+
+# ---- the librosa restatement (N3 row) against a third-party port of the same functions -------------------------------
+def test_librosa_restatement_against_transformers_audio_utils():
+    """oracle/librosa_ref.py (Slaney mel filterbank, centred zero-padded periodic-Hann STFT, power mel spectrogram,
+    power_to_db) against `transformers.audio_utils` -- an independent numpy port of the same librosa functions that
+    happens to be installed in this image (librosa itself is not).  Not our code, not the oracle's author: the
+    closest thing to an external pin this row has."""
+    au = pytest.importorskip("transformers.audio_utils")
+    from oracle import librosa_ref as lr
+    for sr, n_fft, n_mels in ((44100, 2048, 128), (22050, 2048, 128), (44100, 1024, 40)):
+        theirs = au.mel_filter_bank(num_frequency_bins=1 + n_fft // 2, num_mel_filters=n_mels, min_frequency=0.0,
+                                    max_frequency=sr / 2.0, sampling_rate=sr, norm="slaney", mel_scale="slaney")
+        ours = lr.mel(sr=sr, n_fft=n_fft, n_mels=n_mels)
+        assert theirs.shape == ours.T.shape
+        np.testing.assert_array_equal(theirs != 0, ours.T != 0)                       # same support
+        np.testing.assert_allclose(ours.T, theirs, rtol=2e-5, atol=1e-9)              # float32 table against float64
+    y = synth_guitar(4100, 2.0)
+    mel = au.mel_filter_bank(num_frequency_bins=1025, num_mel_filters=128, min_frequency=0.0, max_frequency=SR / 2.0,
+                             sampling_rate=SR, norm="slaney", mel_scale="slaney")
+    theirs_db = au.spectrogram(y.astype(np.float64), au.window_function(2048, "hann", periodic=True), frame_length=2048,
+                               hop_length=512, power=2.0, center=True, pad_mode="constant", mel_filters=mel,
+                               mel_floor=1e-10, log_mel="dB", reference=1.0, min_value=1e-10, db_range=None,
+                               dtype=np.float64).T
+    ours_db = lr.power_to_db(lr.melspectrogram(y, sr=SR), top_db=None)
+    assert theirs_db.shape == ours_db.shape == (1 + len(y) // 512, 128)
+    np.testing.assert_allclose(ours_db, theirs_db, rtol=0, atol=2e-3)                 # dB; float32 einsum in the restatement
+    # power_to_db with a range clip == librosa's top_db
+    np.testing.assert_allclose(lr.power_to_db(lr.melspectrogram(y, sr=SR), top_db=80.0),
+                               au.power_to_db(lr.melspectrogram(y, sr=SR).astype(np.float64), reference=1.0, min_value=1e-10,
+                                              db_range=80.0), rtol=0, atol=1e-4)
