@@ -321,6 +321,13 @@ int build_res(b200spec_plan *pl, const b200spec_res_desc &d, ResPlan &r) {
   return 0;
 }
 
+// frames per task of the one-launch kernel: its point is that a chunk's samples are still in L2 when the second and third
+// resolution read them, so the chunks of all resident groups (444 x chunk x 441 samples) must fit L2 with room to spare
+#ifndef B2_MULTI_CHUNK_MAX
+#define B2_MULTI_CHUNK_MAX 48
+#endif
+constexpr long long kMultiChunkMax = B2_MULTI_CHUNK_MAX;
+
 struct Workspace {
   int *counter;
   int *task_off;
@@ -661,7 +668,7 @@ int b200spec_logfilt_multi(const b200spec_plan *plan, int32_t n_res, const int32
   const long long slots = (long long)plan->num_sms * b2::kMultiGroups;
   long long chunk = total_frames / (slots * 8);
   if (chunk < 16) chunk = 16;
-  if (chunk > 96) chunk = 96;
+  if (chunk > kMultiChunkMax) chunk = kMultiChunkMax;
   if (chunk >= 16) chunk -= (chunk + kd_max) % 4;
   b2::k_setup_tasks<<<1, 1024, 0, st>>>(reinterpret_cast<const long long *>(d_frame_off), n_clips, (int)chunk,
                                          w.task_off, w.counter);
