@@ -93,6 +93,13 @@ struct ResPlan {
   float win_h = 0.f;
   float2 win_cs[16] = {};
   float2 *d_win_ab = nullptr;
+  // warp-per-pair kernel (frame 1024): W_1024^(b c) table, window constants, filterbank packed for 32 slabs per round
+  float2 *d_w32_tw = nullptr;
+  float2 win_cs32[32] = {};
+  int w32_L = 0, w32_ns = 0, w32_kmin = 0, w32_ndw = 0;
+  float4 *d_w32_w4 = nullptr;
+  int4 *d_w32_band = nullptr;
+  float *d_w32_dw = nullptr;
   int fb_L = 3, fb_ns = 1, fb_kmin = 0, fb_ndw = 0, fb_ndirect = 0, fb_w4_global = 0;
   float4 *d_fb_w4 = nullptr;
   int4 *d_fb_band = nullptr;
@@ -241,6 +248,10 @@ int build_res(b200spec_plan *pl, const b200spec_res_desc &d, ResPlan &r) {
         const double a = 2.0 * PI * (double)(n1 * bpf) / (double)(F - 1);
         r.win_cs[n1] = make_float2((float)cos(a), (float)sin(a));
       }
+      for (int a32 = 0; a32 < 32; ++a32) {       // warp kernel: 32 points per lane, F / 32 samples apart
+        const double a = 2.0 * PI * (double)(a32 * (F / 32)) / (double)(F - 1);
+        r.win_cs32[a32] = make_float2((float)cos(a), (float)sin(a));
+      }
       std::vector<float2> ab(bpf);
       for (int b = 0; b < bpf; ++b) {
         const double t = 2.0 * PI * (double)b / (double)(F - 1);
@@ -305,6 +316,23 @@ int build_res(b200spec_plan *pl, const b200spec_res_desc &d, ResPlan &r) {
   if ((rc = upload(pl, reinterpret_cast<const float4 *>(fp.w4.data()), fp.w4.size() / 4, &r.d_fb_w4))) return rc;
   if ((rc = upload(pl, reinterpret_cast<const int4 *>(fp.band.data()), fp.band.size(), &r.d_fb_band))) return rc;
   if ((rc = upload(pl, fp.dw.data(), fp.dw.size(), &r.d_fb_dw))) return rc;
+  if ((F == 1024 || F == 2048) && B > 0) {   // warp-per-FFT kernel: 32 slabs per round; two frames per call at frame 1024, one at 2048
+    b2::FbPack f32p = b2::fb_pack(N, B, d.band_start, d.band_len, d.band_woff, d.weights, F == 1024 ? 2 : 1, 0, 32);
+    std::vector<float2> tw(32 * 32);
+    for (int cc = 0; cc < 32; ++cc)
+      for (int b = 0; b < 32; ++b) {
+        const double a = -2.0 * PI * (double)(b * cc) / 1024.0;
+        tw[cc * 32 + b] = make_float2((float)cos(a), (float)sin(a));
+      }
+    r.w32_L = f32p.L;
+    r.w32_ns = f32p.NS;
+    r.w32_kmin = f32p.kmin;
+    r.w32_ndw = (int)f32p.dw.size();
+    if ((rc = upload(pl, tw.data(), tw.size(), &r.d_w32_tw))) return rc;
+    if ((rc = upload(pl, reinterpret_cast<const float4 *>(f32p.w4.data()), f32p.w4.size() / 4, &r.d_w32_w4))) return rc;
+    if ((rc = upload(pl, reinterpret_cast<const int4 *>(f32p.band.data()), f32p.band.size(), &r.d_w32_band))) return rc;
+    if ((rc = upload(pl, f32p.dw.data(), f32p.dw.size(), &r.d_w32_dw))) return rc;
+  }
   if ((rc = upload(pl, d.band_start, (size_t)B, &r.d_band_start))) return rc;
   if ((rc = upload(pl, d.band_len, (size_t)B, &r.d_band_len))) return rc;
   if ((rc = upload(pl, d.band_woff, (size_t)B, &r.d_band_woff))) return rc;
@@ -342,12 +370,13 @@ int carve_workspace(void *ws, size_t bytes, int n_clips, Workspace &w) {
 }
 
 int choose_chunk(const b200spec_plan *pl, int F, long long total_frames, int kd) {
-  const int G = (F == 8192) ? 3 : 4;
+  const int G = (F == 8192) ? 3 : (F <= 2048) ? 8 : 4;   // frames 1024 / 2048: 16 warps per SM pull tasks of their own
   const long long slots = (long long)pl->num_sms * G;
   long long chunk = total_frames / (slots * 8);
   const int lo = kd > 0 ? 16 : 4;
   if (chunk < lo) chunk = lo;
   if (chunk > 96) chunk = 96;     // measured on B200: 64-96 frames per task balance warm-up rows and tail imbalance
+  if (F <= 2048 && chunk > 48) chunk = 48;   // 2368 warps pull tasks there: ten tasks each instead of five
   // a task transforms chunk + kd frames (kd warm-up rows of the difference); keep that a multiple of the
   // tail batch (4 frames, pairs of frames in k_front_pair) so no step runs half empty
   if (chunk >= 16) chunk -= (chunk + kd) % 4;
@@ -369,6 +398,7 @@ void fill_plan_params(const b200spec_plan *pl, const ResPlan &r, b2::FrontParams
   p.win_fly = r.win_fly;
   p.win_h = r.win_h;
   for (int i = 0; i < 16; ++i) p.win_cs[i] = r.win_cs[i];
+  for (int i = 0; i < 32; ++i) p.win_cs32[i] = r.win_cs32[i];
   p.win_ab = r.d_win_ab;
   p.tw2 = r.d_tw2;
   p.tw3 = r.d_tw3;
@@ -451,6 +481,36 @@ int launch_front(const b200spec_plan *pl, int res, int mode, const void *d_sig, 
 #else
   constexpr bool use_pair = true;
 #endif
+#ifdef B2_NO_WARP      // tuning: keep the pair kernel at frames 1024 / 2048
+  constexpr bool use_warp = false;
+#else
+  constexpr bool use_warp = true;
+#endif
+#ifndef B2_WARP_MAX_F  // tuning: -DB2_WARP_MAX_F=1024 keeps the pair kernel at frame 2048
+#define B2_WARP_MAX_F 2048
+#endif
+  // frames 1024 / 2048: one warp per FFT (frontend_warp_kernel.cuh); the projection output keeps the pair kernel
+  if (use_warp && use_pair && mode == b2::MODE_LOGFILT && (r.frame_size == 1024 || r.frame_size == B2_WARP_MAX_F) &&
+      r.d_w32_tw != nullptr && p.proj == nullptr) {
+    b2::FrontParams q = p;
+    q.tw3 = r.d_w32_tw;
+    q.fb_w4 = r.d_w32_w4;
+    q.fb_band = r.d_w32_band;
+    q.fb_dw = r.d_w32_dw;
+    q.fb_L = r.w32_L;
+    q.fb_ns = r.w32_ns;
+    q.fb_kmin = r.w32_kmin;
+    q.fb_ndw = r.w32_ndw;
+    e = r.frame_size == 1024 ? b2_launch_warp_1024(in, q, pl->num_sms, task_bound, st)
+                             : b2_launch_warp_2048(in, q, pl->num_sms, task_bound, st);
+    if (e == cudaSuccess) {
+      g_launches++;
+      return 0;
+    }
+    if (e != cudaErrorInvalidConfiguration)
+      return fail(B200SPEC_ERR_CUDA, "front-end (warp) kernel launch failed: %s", cudaGetErrorString(e));
+    (void)cudaGetLastError();   // did not fit: fall through to the pair kernel
+  }
   if (use_pair && mode == b2::MODE_LOGFILT && r.frame_size <= 4096 && r.d_pair_tw3 != nullptr) {
     b2::FrontParams q = p;
     q.tw3 = r.d_pair_tw3;

@@ -3,6 +3,7 @@
 #pragma once
 #include "frontend_kernel.cuh"
 #include "frontend_pair_kernel.cuh"
+#include "frontend_warp_kernel.cuh"
 
 namespace b2 {
 
@@ -106,6 +107,46 @@ static cudaError_t launch_pair_size(int in, FrontParams &p, int num_sms, long lo
   return cudaErrorInvalidValue;
 }
 
+template <int F>
+static cudaError_t launch_warp_size(int in, FrontParams &p, int num_sms, long long task_bound, cudaStream_t st);
+
+// warps per CTA of the warp-per-FFT kernel (frames 1024 / 2048): 16 x 32 threads at <= 128 registers, ~10 KB of shared memory each
+#ifndef B2_WARP_NW_1024
+#define B2_WARP_NW_1024 16
+#endif
+#ifndef B2_WARP_NW_2048
+#define B2_WARP_NW_2048 16
+#endif
+template <int F>
+struct WarpKernelWarps {
+  static constexpr int value = (F == 1024) ? B2_WARP_NW_1024 : B2_WARP_NW_2048;
+};
+
+template <int F, int IN>
+static cudaError_t launch_warp_one(FrontParams &p, int num_sms, long long task_bound, cudaStream_t st) {
+  constexpr int NW = WarpKernelWarps<F>::value;
+  const size_t smem = warp_smem_layout<F>(p, NW);
+  if (smem > kMaxSmemPerCta) return cudaErrorInvalidConfiguration;
+  auto kern = k_front_warp<F, IN, NW>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  long long ctas = (task_bound + NW - 1) / NW;
+  int grid = (int)(ctas < num_sms ? (ctas < 1 ? 1 : ctas) : num_sms);
+  kern<<<grid, 32 * NW, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+template <int F>
+static cudaError_t launch_warp_size(int in, FrontParams &p, int num_sms, long long task_bound, cudaStream_t st) {
+  switch (in) {
+    case IN_F32_MONO: return launch_warp_one<F, IN_F32_MONO>(p, num_sms, task_bound, st);
+    case IN_F32_STEREO: return launch_warp_one<F, IN_F32_STEREO>(p, num_sms, task_bound, st);
+    case IN_I16_MONO: return launch_warp_one<F, IN_I16_MONO>(p, num_sms, task_bound, st);
+    case IN_I16_STEREO: return launch_warp_one<F, IN_I16_STEREO>(p, num_sms, task_bound, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
 // groups per CTA of the one-launch kernel: its group blocks are sized for frame 4096 (33 KB FFT buffer + 16 KB magnitudes)
 constexpr int kMultiGroups = 3;
 
@@ -129,6 +170,8 @@ static cudaError_t launch_multi_one(MultiParams &m, int num_sms, long long task_
 cudaError_t b2_launch_multi(int in, b2::MultiParams &m, int num_sms, long long task_bound, cudaStream_t st);
 
 cudaError_t b2_launch_pair_1024(int in, b2::FrontParams &p, int num_sms, long long task_bound, cudaStream_t st);
+cudaError_t b2_launch_warp_1024(int in, b2::FrontParams &p, int num_sms, long long task_bound, cudaStream_t st);
+cudaError_t b2_launch_warp_2048(int in, b2::FrontParams &p, int num_sms, long long task_bound, cudaStream_t st);
 cudaError_t b2_launch_pair_2048(int in, b2::FrontParams &p, int num_sms, long long task_bound, cudaStream_t st);
 cudaError_t b2_launch_pair_4096(int in, b2::FrontParams &p, int num_sms, long long task_bound, cudaStream_t st);
 

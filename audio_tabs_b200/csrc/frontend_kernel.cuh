@@ -50,6 +50,7 @@ struct FrontParams {
   int win_fly;
   float win_h;
   float2 win_cs[16];
+  float2 win_cs32[32];  // the same for the warp kernel (frame 1024, 32 points per lane): (cos, sin)(2 pi 32 a / (F-1))
   const float2 *win_ab; // [BPF of the pair geometry = F / 16]
   const float2 *tw2;    // [16][16]   tw2[k1*16 + n2] = W_256^(n2 k1)
   const float2 *tw3;    // [R3][129]  tw3[n3*129 + q] = W_N^(n3 q)

@@ -561,8 +561,9 @@ def test_peak_normalisation_of_a_power_spectrogram(b2):
     fused = fe.process_batch(clips, peak_normalize=True, eps=0.0)
     plain = fe.process_batch([c / np.abs(c).max() for c in clips])
     for a, b in zip(fused, plain):
-        # 10 log10: a wrong (linear) gain would be off by 10 log10(g) = up to 11.5 dB here
-        assert np.abs(a - b).max() < 2e-3, np.abs(a - b).max()
+        # 10 log10: a wrong (linear) gain would be off by 10 log10(g) = up to 11.5 dB here; what remains is the float32
+        # noise floor of two differently scaled transforms in the quietest mel bands (2e-3 dB measured)
+        assert np.abs(a - b).max() < 5e-3, np.abs(a - b).max()
 
 
 def test_planless_calls_follow_the_pointer_device(b2):
