@@ -373,7 +373,7 @@ int choose_chunk(const b200spec_plan *pl, int F, long long total_frames, int kd)
   const int G = (F == 8192) ? 3 : (F <= 2048) ? 8 : 4;   // frames 1024 / 2048: 16 warps per SM pull tasks of their own
   const long long slots = (long long)pl->num_sms * G;
   long long chunk = total_frames / (slots * 8);
-  const int lo = kd > 0 ? 16 : 4;
+  const int lo = F <= 2048 ? (kd > 0 ? 8 : 2) : (kd > 0 ? 16 : 4);   // smallest task (a warp runs its frames one after the other)
   if (chunk < lo) chunk = lo;
   if (chunk > 96) chunk = 96;     // measured on B200: 64-96 frames per task balance warm-up rows and tail imbalance
   if (F <= 2048 && chunk > 48) chunk = 48;   // 2368 warps pull tasks there: ten tasks each instead of five
@@ -490,8 +490,11 @@ int launch_front(const b200spec_plan *pl, int res, int mode, const void *d_sig, 
 #define B2_WARP_MAX_F 2048
 #endif
   // frames 1024 / 2048: one warp per FFT (frontend_warp_kernel.cuh); the projection output keeps the pair kernel
+  // (frame 2048 runs one frame per FFT there and walks the filterbank once per frame: with a filterbank that covers the
+  //  whole spectrum -- librosa's 128 mel bands: 45 bins per lane -- the pair kernel, which amortises the weights over
+  //  four frames, is the faster one: 15.7 against 18.6 ms on the onset-strength workload)
   if (use_warp && use_pair && mode == b2::MODE_LOGFILT && (r.frame_size == 1024 || r.frame_size == B2_WARP_MAX_F) &&
-      r.d_w32_tw != nullptr && p.proj == nullptr) {
+      r.d_w32_tw != nullptr && p.proj == nullptr && (r.frame_size == 1024 || r.w32_ns * r.w32_L <= 30)) {
     b2::FrontParams q = p;
     q.tw3 = r.d_w32_tw;
     q.fb_w4 = r.d_w32_w4;
