@@ -9,7 +9,7 @@ import ctypes as C
 import os
 from pathlib import Path
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_RES = 4
 MAX_DIFF_FRAMES = 16
 
@@ -48,6 +48,7 @@ class ResDesc(C.Structure):
         ("log_scale", C.c_float),
         ("log_floor", C.c_float),
         ("circular_shift", C.c_int32),
+        ("include_nyquist", C.c_int32),
     ]
 
 

@@ -242,8 +242,32 @@ class StackedDifference(_Stage):
         return (t, 2 * b)
 
 
+class BufferedDifference(_Stage):
+    """Result of an online (``reset=False``) SpectrogramDifferenceProcessor call: rows already computed on the device."""
+
+    def __init__(self, tensor, like, diff_frames, spectrogram=None):
+        self._tensor = tensor
+        self.source = like
+        self.stft = like.stft
+        self.spectrogram = spectrogram if spectrogram is not None else like
+        self.filterbank = getattr(like, "filterbank", None)
+        self.bin_frequencies = like.bin_frequencies
+        self.diff_frames = diff_frames
+
+    def _compute_tensor(self):
+        return self._tensor
+
+    def _result_shape(self):
+        return tuple(self._tensor.shape)
+
+
 class SpectrogramDifferenceProcessor(Processor):
-    """Offline behaviour of madmom's processor (``reset=True``): the first ``diff_frames`` rows are 0."""
+    """madmom's SpectrogramDifferenceProcessor.  ``reset=True`` (the default, what every caller of the reference
+    uses) is the offline behaviour: the first ``diff_frames`` rows of the difference are 0 and the whole chain is
+    one fused launch.  ``reset=False`` continues from the rows of the previous calls like madmom's BufferProcessor
+    does: the buffer is as long as the first call's rows plus ``diff_frames``, new rows are shifted in at its end
+    and the result covers the whole buffer behind its first ``diff_frames`` rows (difference kernel on the
+    device-resident buffer)."""
 
     def __init__(self, diff_ratio=DIFF_RATIO, diff_frames=DIFF_FRAMES, diff_max_bins=DIFF_MAX_BINS,
                  positive_diffs=POSITIVE_DIFFS, stack_diffs=None, **kwargs):
@@ -260,9 +284,39 @@ class SpectrogramDifferenceProcessor(Processor):
         self.__dict__.update(state)
         self._buffer = None
 
+    def _history(self, num_bands):
+        """The buffer as a device tensor (diff_frames + T0, B): inf rows, then the rows seen so far."""
+        import torch
+        kind, held = self._buffer
+        if kind == "rows":
+            return held
+        first = held.tensor()                       # the offline call's spectrogram rows
+        if first.ndim != 2 or first.shape[1] != num_bands:
+            raise ValueError("could not broadcast input array from shape (%d,) into shape (%d,)"
+                             % (num_bands, first.shape[-1]))
+        init = torch.full((self.diff_frames, num_bands), float("inf"), dtype=torch.float32, device=first.device)
+        return torch.cat((init, first.to(torch.float32)))
+
+    def _process_online(self, data, args):
+        import torch
+        from ..engine import buffered_difference
+        x = data.tensor()
+        buf = self._history(x.shape[1])
+        n = x.shape[0]
+        if n > buf.shape[0]:                        # madmom: buffer[-n:] = data does not fit
+            raise ValueError("could not broadcast input array from shape (%d,%d) into shape (%d,%d)"
+                             % (n, x.shape[1], buf.shape[0], buf.shape[1]))
+        buf = torch.cat((buf[n:], x.to(device=buf.device, dtype=torch.float32)))
+        self._buffer = ("rows", buf)
+        kd = self.diff_frames
+        stacked = self.stack_diffs is np.hstack
+        out = buffered_difference(buf, kd, bool(args["positive_diffs"]), int(args["diff_max_bins"] or 0), stacked)
+        if self.stack_diffs is None or stacked:
+            return BufferedDifference(out, data, kd)
+        B = buf.shape[1]
+        return self.stack_diffs((buf[kd:].cpu().numpy(), out[:, -B:].cpu().numpy()))
+
     def process(self, data, reset=True, **kwargs):
-        if not reset:
-            raise ValueError("online mode (reset=False) is not implemented on the device")
         args = dict(diff_ratio=self.diff_ratio, diff_frames=self.diff_frames, diff_max_bins=self.diff_max_bins,
                     positive_diffs=self.positive_diffs)
         args.update(kwargs)
@@ -271,6 +325,9 @@ class SpectrogramDifferenceProcessor(Processor):
             self.diff_frames = _diff_frames(args["diff_ratio"], frame_size=data.stft.frames.frame_size,
                                             hop_size=data.stft.frames.hop_size, window=data.stft.window)
             args["diff_frames"] = self.diff_frames
+        if not reset and self._buffer is not None:
+            return self._process_online(data, args)
+        self._buffer = ("stage", data)      # these rows are the history of a later reset=False call (nothing is computed now)
         diff = SpectrogramDifference(data, **args)
         if self.stack_diffs is None:
             return diff

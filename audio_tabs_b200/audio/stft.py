@@ -59,17 +59,20 @@ class ShortTimeFourierTransform(LazyArray):
                              "as fft_size for another frame_size" % fft_size)
         if circular_shift and fft_size != frame_size:
             raise ValueError("circular_shift=True with fft_size != frame_size is not supported by the CUDA path")
-        if include_nyquist:
-            raise ValueError("include_nyquist=True is not supported by the CUDA path")
         self.frames = frames
         self.window = window
         self.fft_window = fft_window
         self.fft_size = fft_size
         self.circular_shift = bool(circular_shift)
-        self.include_nyquist = include_nyquist
+        self.include_nyquist = bool(include_nyquist)
         self.fftw = None
-        self.bin_frequencies = fft_frequencies(fft_size >> 1, frames.signal.sample_rate) \
-            if frames.signal.sample_rate else np.arange(fft_size >> 1, dtype=float)
+        nb = (fft_size >> 1) + int(self.include_nyquist)
+        if not frames.signal.sample_rate:
+            self.bin_frequencies = np.arange(nb, dtype=float)
+        elif self.include_nyquist:
+            self.bin_frequencies = np.fft.rfftfreq(fft_size, 1.0 / frames.signal.sample_rate)
+        else:
+            self.bin_frequencies = fft_frequencies(fft_size >> 1, frames.signal.sample_rate)
 
     def kernel_window_and_origin(self):
         """(window of fft_size points, origin) that make the kernel's frame [int(n hop) - fft_size/2 - origin, + fft_size)
@@ -85,7 +88,7 @@ class ShortTimeFourierTransform(LazyArray):
         return win, self.frames.origin + frame_size // 2 - self.fft_size // 2
 
     def _result_shape(self):
-        return (self.frames.num_frames, self.fft_size >> 1)
+        return (self.frames.num_frames, self.num_bins)
 
     @property
     def num_frames(self):
@@ -93,7 +96,7 @@ class ShortTimeFourierTransform(LazyArray):
 
     @property
     def num_bins(self):
-        return self.fft_size >> 1
+        return (self.fft_size >> 1) + int(self.include_nyquist)
 
     def _compute_tensor(self):
         from ..engine import run_chain

@@ -83,7 +83,7 @@ struct ResPlan {
   float mul = 1.f, add = 1.f;
   int power = 0;
   float log_scale = 1.f, log_floor = 0.f;
-  int diff_frames = 0, positive = 0, diff_max_bins = 0, circular_shift = 0;
+  int diff_frames = 0, positive = 0, diff_max_bins = 0, circular_shift = 0, include_nyquist = 0;
   int num_classes = 0, nproj = 0;
   // device tables
   float *d_window = nullptr;
@@ -163,6 +163,9 @@ int build_res(b200spec_plan *pl, const b200spec_res_desc &d, ResPlan &r) {
   if (d.diff_max_bins < 0 || d.diff_max_bins > 64) return fail(B200SPEC_ERR_UNSUPPORTED, "diff_max_bins %d outside [0, 64]", d.diff_max_bins);
   r.diff_max_bins = d.diff_max_bins > 1 ? d.diff_max_bins : 0;
   r.circular_shift = d.circular_shift != 0;
+  r.include_nyquist = d.include_nyquist != 0;
+  if (r.include_nyquist && d.num_bands > 0)
+    return fail(B200SPEC_ERR_UNSUPPORTED, "include_nyquist: a filterbank takes frame_size/2 bins, not frame_size/2 + 1");
   r.num_bands = d.num_bands;
   r.num_classes = d.num_classes;
   if (d.num_classes > 0) {   // validated before anything reads proj_off (the shared-memory probe below does)
@@ -425,6 +428,7 @@ void fill_plan_params(const b200spec_plan *pl, const ResPlan &r, b2::FrontParams
   p.diff_frames = r.diff_frames;
   p.positive = r.positive;
   p.circular_shift = r.circular_shift;
+  p.spec_ld = r.frame_size / 2 + (r.include_nyquist ? 1 : 0);
   p.proj_off = r.d_proj_off;
   p.proj_band = r.d_proj_band;
   p.proj_w = r.d_proj_w;

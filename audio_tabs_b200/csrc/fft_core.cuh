@@ -385,8 +385,9 @@ B2_HD void fft_pass3_special(const float2 *buf, const float2 *tw3, const float2 
 //   h = lane / R3 (0: q = 0, 1: q = 128), k3 = lane % R3, bin k = 128 h + 256 k3
 //   X[k] = E + pt[k] D,  E = 2 sum_n w_n Re(c_n),  D = 2 i sum_n w_n Im(c_n),
 //   w_n = W_(2 R3)^(n (2 k3 + h)) = wr[(n (2 k3 + h)) mod 2 R3],  c_n = element n of column q.
+// mirror = X[N - k] = conj(E - pt[k] D): for lane 0 (k = 0) the Nyquist bin X[N].
 template <int F>
-B2_HD float2 fft_pass3_selfpaired(int lane, const float2 *buf, const float2 *wr, const float2 *pt, int &bin) {
+B2_HD float2 fft_pass3_selfpaired(int lane, const float2 *buf, const float2 *wr, const float2 *pt, int &bin, float2 &mirror) {
   using C = FftCfg<F>;
   constexpr int R3 = C::R3;
   const int h = lane / R3, k3 = lane % R3;
@@ -406,7 +407,14 @@ B2_HD float2 fft_pass3_selfpaired(int lane, const float2 *buf, const float2 *wr,
   }
   const float2 T = cmul(make_float2(-2.f * D.y, 2.f * D.x), pt[k3 * 129 + 128 * h]);
   bin = 128 * h + 256 * k3;
+  mirror = make_float2(fmaf(2.f, E.x, -T.x), fmaf(-2.f, E.y, T.y));
   return make_float2(fmaf(2.f, E.x, T.x), fmaf(2.f, E.y, T.y));
+}
+
+template <int F>
+B2_HD float2 fft_pass3_selfpaired(int lane, const float2 *buf, const float2 *wr, const float2 *pt, int &bin) {
+  float2 mirror;
+  return fft_pass3_selfpaired<F>(lane, buf, wr, pt, bin, mirror);
 }
 
 // =================================================================================================

@@ -84,7 +84,8 @@ struct FrontParams {
   float *proj;
   long long ld_proj;
   // outputs (MODE_SPECTRUM)
-  float *spec_out;      // (rows, N) float or float2
+  float *spec_out;      // (rows, spec_ld) float or float2
+  int spec_ld;          // N, or N + 1 with the Nyquist bin (madmom include_nyquist)
   int spec_complex;
   int circular_shift;   // madmom stft(circular_shift=True) with fft_size == frame_size: the two halves of the windowed
                         // frame are swapped before the transform = bin k times (-1)^k (magnitudes are unchanged)
@@ -574,24 +575,28 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
           } else if (frame >= f0) {
             const long long row = row0 + frame;
             if (p.spec_complex) {
-              float2 *o = reinterpret_cast<float2 *>(p.spec_out) + row * N;
+              float2 *o = reinterpret_cast<float2 *>(p.spec_out) + row * p.spec_ld;
               if (u != 0)
                 fft_pass3_unit<F>(u, fbuf + pa_off, fbuf + pb_off, s_tw3 + u, s_pt + u,
                                   [&](int k, float2 X) { o[k] = (p.circular_shift && (k & 1)) ? make_float2(-X.x, -X.y) : X; });
               if (tid < 2 * R3) {
                 int bin;
-                const float2 X = fft_pass3_selfpaired<F>(tid, fbuf, s_wr, s_pt, bin);
+                float2 Xm;
+                const float2 X = fft_pass3_selfpaired<F>(tid, fbuf, s_wr, s_pt, bin, Xm);
                 o[bin] = (p.circular_shift && (bin & 1)) ? make_float2(-X.x, -X.y) : X;
+                if (tid == 0 && p.spec_ld > N) o[N] = Xm;     // Nyquist bin: the mirror of bin 0 (N is even: no sign flip)
               }
             } else {
-              float *o = p.spec_out + row * N;
+              float *o = p.spec_out + row * p.spec_ld;
               if (u != 0)
                 fft_pass3_unit<F>(u, fbuf + pa_off, fbuf + pb_off, s_tw3 + u, s_pt + u,
                                   [&](int k, float2 X) { o[k] = cabs_fast(X); });
               if (tid < 2 * R3) {
                 int bin;
-                const float2 X = fft_pass3_selfpaired<F>(tid, fbuf, s_wr, s_pt, bin);
+                float2 Xm;
+                const float2 X = fft_pass3_selfpaired<F>(tid, fbuf, s_wr, s_pt, bin, Xm);
                 o[bin] = cabs_fast(X);
+                if (tid == 0 && p.spec_ld > N) o[N] = cabs_fast(Xm);
               }
             }
           }

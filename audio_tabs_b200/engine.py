@@ -89,6 +89,7 @@ def _spec_from(rec, stft=None, frame_size=None):
         win, origin = stft.kernel_window_and_origin()
         return ResolutionSpec(frame_size=stft.fft_size, hop_size=stft.frames.hop_size,
                               origin=origin, fft_window=win, circular_shift=stft.circular_shift,
+                              include_nyquist=stft.include_nyquist,
                               filterbank=rec["filterbank"], log=rec["log"] is not None, mul=mul, add=add,
                               log_scale=rec["log_scale"], diff_frames=diff_frames, positive_diffs=positive,
                               diff_max_bins=max_bins, **fold)
@@ -122,6 +123,22 @@ def _standalone_tail(plan, spec, x, rec, device):
     od.col_spec, od.col_diff = (0, B) if rec["stack"] else (-1, 0)
     fo = _frame_off(T, device)
     _ffi.check(lib.b200spec_diff_flux_chroma(plan.handle, 0, _ptr(x), B, _ptr(fo), 1, T, C.byref(od), stream))
+    return out
+
+
+def buffered_difference(buf, diff_frames, positive, max_bins, stacked):
+    """Online SpectrogramDifferenceProcessor: the lagged difference of a device-resident buffer (diff_frames + T, B)
+    whose first rows may be +inf ("no history yet": those differences are 0, madmom sets inf differences to 0).
+    Returns rows diff_frames.. of [spec | diff] (stacked) or of the diff alone."""
+    device = buf.device
+    rec = dict(filterbank=None, log=None, log_scale=1.0, diff=(int(diff_frames), bool(positive), int(max_bins)),
+               stack=bool(stacked))
+    spec = _spec_from(rec, frame_size=2048)
+    plan = get_plan(device.index, "f32", 1, [spec])
+    out = _standalone_tail(plan, spec, buf.contiguous(), rec, device)[diff_frames:]
+    B = buf.shape[1]
+    d = out[:, -B:]
+    d.masked_fill_(torch.isinf(d), 0.0)
     return out
 
 

@@ -56,6 +56,7 @@ class ResolutionSpec:
     log_scale: float = 1.0                      # out = log_scale * log10(max(mul*y + add, log_floor))
     log_floor: float = 0.0                      # <= 0: no clamp (madmom); librosa power_to_db: amin = 1e-10
     circular_shift: bool = False                # STFT of the half-swapped frame: bin k times (-1)^k (complex output only)
+    include_nyquist: bool = False               # STFT / magnitude rows carry frame_size/2 + 1 bins (no filterbank then)
     proj_classes: Optional[np.ndarray] = None   # per band class index (or -1), e.g. chroma fold
     proj_matrix: Optional[np.ndarray] = None    # or a dense (B, C) projection
     num_classes: int = 0
@@ -73,6 +74,9 @@ class ResolutionSpec:
         self.window32 = np.ascontiguousarray(win, dtype=np.float32)
         if self.filterbank is not None and not isinstance(self.filterbank, Filterbank):
             raise TypeError("not a Filterbank type or instance: %s" % self.filterbank)
+        if self.filterbank is not None and self.include_nyquist:
+            raise ValueError("include_nyquist=True: the filterbank kernels take frame_size/2 bins; "
+                             "filter a spectrogram without the Nyquist bin")
         if self.filterbank is not None and self.filterbank.shape[0] != self.frame_size // 2:
             raise ValueError("filterbank must have frame_size/2 bins")
         self.num_bands = 0 if self.filterbank is None else int(self.filterbank.shape[1])
@@ -101,7 +105,7 @@ class ResolutionSpec:
             _digest(None if self.filterbank is None else np.asarray(self.filterbank)),
             int(self.log), repr(float(self.mul)), repr(float(self.add)), self.diff_frames,
             int(self.positive_diffs), int(self.diff_max_bins or 0), int(bool(self.power)),
-            repr(float(self.log_scale)), repr(float(self.log_floor)), int(bool(self.circular_shift)),
+            repr(float(self.log_scale)), repr(float(self.log_floor)), int(bool(self.circular_shift)), int(bool(self.include_nyquist)),
             _digest(self.proj_off, self.proj_band, self.proj_weight))))
 
     @property
@@ -153,6 +157,7 @@ class DevicePlan:
             r.diff_max_bins = int(s.diff_max_bins or 0)
             r.power, r.log_scale, r.log_floor = int(bool(s.power)), float(s.log_scale), float(s.log_floor)
             r.circular_shift = int(bool(s.circular_shift))
+            r.include_nyquist = int(bool(s.include_nyquist))
             r.num_classes = int(s.num_classes) if s.proj_off is not None else 0
             if s.proj_off is not None:
                 r.proj_off, r.proj_band, r.proj_weight = iptr(s.proj_off), iptr(s.proj_band), fptr(s.proj_weight)
@@ -447,10 +452,12 @@ class FrontEnd:
     def stft_packed(self, packed: Packed, res: int = 0, complex_out: bool = True) -> torch.Tensor:
         s = self.specs[res]
         if complex_out:
-            out = torch.empty((packed.total_frames, s.num_bins), dtype=torch.complex64, device=self.device)
+            out = torch.empty((packed.total_frames, s.num_bins + int(s.include_nyquist)), dtype=torch.complex64,
+                              device=self.device)
             fn = self._lib.b200spec_stft
         else:
-            out = torch.empty((packed.total_frames, s.num_bins), dtype=torch.float32, device=self.device)
+            out = torch.empty((packed.total_frames, s.num_bins + int(s.include_nyquist)), dtype=torch.float32,
+                              device=self.device)
             fn = self._lib.b200spec_spectrogram
         ws = self._workspace(res, packed.n_clips)
         _ffi.check(fn(self.plan.handle, res, _ptr(packed.sig), _ptr(packed.clip_off), _ptr(packed.frame_off),

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define B200SPEC_ABI_VERSION 5
+#define B200SPEC_ABI_VERSION 6
 #define B200SPEC_MAX_RES 4          /* resolutions per plan (RNNBeatProcessor uses 3) */
 #define B200SPEC_MAX_DIFF_FRAMES 16 /* largest supported diff lag in frames */
 
@@ -109,6 +109,9 @@ typedef struct b200spec_res_desc {
   /* madmom stft(circular_shift=True) with fft_size == frame_size: the halves of the windowed frame are swapped before
    * the transform, i.e. bin k of b200spec_stft's output is multiplied by (-1)^k.  Magnitude outputs do not change. */
   int32_t circular_shift;
+  /* madmom stft(include_nyquist=True): b200spec_stft / b200spec_spectrogram rows hold frame_size/2 + 1 bins, the last
+   * one the (real) Nyquist bin.  Resolutions with a filterbank take frame_size/2 bins: the two do not combine. */
+  int32_t include_nyquist;
 } b200spec_res_desc;
 
 typedef struct b200spec_plan_desc {
@@ -168,6 +171,7 @@ size_t b200spec_workspace_bytes(int32_t n_clips);
  *   d_frame_off  n_clips+1 row offsets of each clip's first frame in d_out
  *   total_frames d_frame_off[n_clips] (host copy, sizes the grid)
  *   d_out        (total_frames, frame_size/2) complex64 as interleaved float pairs
+ *                (frame_size/2 + 1 bins per row when the resolution was planned with include_nyquist)
  */
 int b200spec_stft(const b200spec_plan *plan, int32_t res, const void *d_sig, const int64_t *d_clip_off,
                   const int64_t *d_frame_off, int32_t n_clips, int64_t total_frames, float *d_out,

@@ -658,8 +658,41 @@ class LogarithmicFilteredSpectrogramProcessor(Processor):
         return self.logp(self.filt(data))
 
 
+class BufferProcessor(Processor):
+    """madmom.processors.BufferProcessor: a fixed-length buffer; new rows are shifted in at the end."""
+
+    def __init__(self, buffer_size=None, init=None, init_value=0):
+        if buffer_size is None and init is not None:
+            buffer_size = init.shape
+        elif isinstance(buffer_size, (int, np.integer)):
+            buffer_size = (buffer_size,)
+        if buffer_size is not None and init is None:
+            init = np.ones(buffer_size) * init_value
+        self.buffer_size = buffer_size
+        self.init = init
+        self.data = init
+
+    def reset(self, init=None):
+        self.data = init if init is not None else self.init
+
+    def process(self, data, **kwargs):
+        ndmin = len(self.buffer_size)
+        if data.ndim < ndmin:
+            data = np.array(data, subok=True, ndmin=ndmin)
+        data_length = len(data)
+        # remove `data_length` rows at the beginning, append the new data (a longer block does not fit: numpy raises)
+        self.data = np.roll(self.data, -data_length, axis=0)
+        self.data[-data_length:] = data
+        return self.data
+
+
 class SpectrogramDifferenceProcessor(Processor):
-    """Offline (reset=True) behaviour: rows n < diff_frames of the diff are 0."""
+    """madmom.audio.spectrogram.SpectrogramDifferenceProcessor.process(data, reset=True).
+
+    reset=True (offline): `diff_frames` rows of inf are put before the data, so rows n < diff_frames of the
+    diff come out 0.  reset=False (online): the rows of the previous calls, kept by a BufferProcessor as long as
+    the FIRST call's data plus diff_frames, are the history of the new rows; the result covers the whole buffer
+    behind its first diff_frames rows."""
 
     def __init__(self, diff_ratio=0.5, diff_frames=None, diff_max_bins=None,
                  positive_diffs=False, stack_diffs=None, **kwargs):
@@ -668,8 +701,9 @@ class SpectrogramDifferenceProcessor(Processor):
         self.diff_max_bins = diff_max_bins
         self.positive_diffs = positive_diffs
         self.stack_diffs = stack_diffs
+        self._buffer = None
 
-    def process(self, data, **kwargs):
+    def process(self, data, reset=True, **kwargs):
         if self.diff_frames is None:
             self.diff_frames = diff_frames_for(self.diff_ratio,
                                                frame_size=data.stft.frames.frame_size,
@@ -677,15 +711,20 @@ class SpectrogramDifferenceProcessor(Processor):
                                                window=data.stft.window)
         k = self.diff_frames
         spec = data.data
-        init = np.full((k, spec.shape[1]), np.nan, dtype=spec.dtype)
-        padded = np.concatenate((init, spec), axis=0)
+        if self._buffer is None or reset:
+            init = np.empty((k, spec.shape[1]), dtype=spec.dtype)
+            init[:] = np.inf
+            rows = np.insert(spec, 0, init, axis=0)
+            self._buffer = BufferProcessor(init=rows)
+        else:
+            rows = self._buffer(spec)
         with np.errstate(invalid="ignore"):
-            diff = spectrogram_difference(padded, k, self.diff_max_bins, self.positive_diffs)[k:]
-        diff[np.isnan(diff)] = 0
+            diff = spectrogram_difference(rows, k, self.diff_max_bins, self.positive_diffs)[k:]    # keep_dims=False
+        diff[np.isinf(diff)] = 0
         if self.stack_diffs is None:
             return _Spec(diff, stft=data.stft, bin_frequencies=data.bin_frequencies,
                          diff_frames=k)
-        return self.stack_diffs((spec, diff))
+        return self.stack_diffs((rows[k:], diff))
 
 
 # ----------------------------------------------------------------------------

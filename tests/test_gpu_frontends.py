@@ -135,6 +135,46 @@ def test_diff_only_and_unstacked(b2):
     assert_close(np.asarray(mk(np.vstack)(sig)), np.vstack((spec, want)), what="custom stack fn")
 
 
+@pytest.mark.parametrize("max_bins,positive,stack", [(None, True, np.hstack), (3, True, None), (None, False, np.hstack),
+                                                      (None, True, np.vstack)])
+def test_online_difference_processor_continues_from_previous_rows(b2, max_bins, positive, stack):
+    """SpectrogramDifferenceProcessor(..., reset=False): madmom's BufferProcessor semantics -- the buffer is as
+    long as the first call's rows + diff_frames, later blocks are shifted in and differenced against the rows
+    of the calls before; a block longer than the buffer does not fit (numpy's broadcast error)."""
+    from audio_tabs_b200.synth import synth_guitar
+    blocks = [synth_guitar(4100 + i, sec) for i, sec in enumerate((0.5, 0.2, 0.01, 0.5, 0.33))]
+
+    def front(m):
+        return m.SequentialProcessor((
+            m.SignalProcessor(num_channels=1, sample_rate=SR), m.FramedSignalProcessor(frame_size=2048, fps=100),
+            m.ShortTimeFourierTransformProcessor(), m.FilteredSpectrogramProcessor(num_bands=12, fmin=30, fmax=17000),
+            m.LogarithmicSpectrogramProcessor(mul=1, add=1)))
+
+    def values(y):
+        return np.asarray(y.data if hasattr(y, "data") and not isinstance(y, np.ndarray) else y)
+
+    kw = dict(diff_ratio=0.5, diff_max_bins=max_bins, positive_diffs=positive, stack_diffs=stack)
+    ours, theirs = b2.SpectrogramDifferenceProcessor(**kw), ref.SpectrogramDifferenceProcessor(**kw)
+    fo, fr = front(b2), front(ref)
+    for i, x in enumerate(blocks):
+        reset = i == 0
+        got, want = values(ours(fo(x), reset=reset)), values(theirs(fr(x), reset=reset))
+        assert got.shape == want.shape, (i, got.shape, want.shape)
+        assert np.isfinite(got).all()
+        assert_close(got, want, what="online block %d" % i)
+    # a first call with reset=False starts like an offline call
+    fresh = b2.SpectrogramDifferenceProcessor(**kw)
+    assert_close(values(fresh(fo(blocks[1]), reset=False)),
+                 values(ref.SpectrogramDifferenceProcessor(**kw)(fr(blocks[1]), reset=True)), what="first online call")
+    # ... and its buffer is only as long as that first block (+ diff_frames): a longer block is refused
+    with pytest.raises(ValueError, match="could not broadcast"):
+        fresh(fo(blocks[0]), reset=False)
+    with pytest.raises(ValueError, match="could not broadcast"):
+        short = ref.SpectrogramDifferenceProcessor(**kw)
+        short(fr(blocks[1]), reset=False)
+        short(fr(blocks[0]), reset=False)
+
+
 # ---- batch engine: formats, ragged batches, flux -----------------------------------------------
 def _oracle_beat(x):
     return ref.rnn_beat_preprocessor()(x)
@@ -740,6 +780,46 @@ def test_circular_shift(b2, frame_size):
     with pytest.raises(ValueError):
         b2.ShortTimeFourierTransform(b2.FramedSignal(b2.Signal(x, sample_rate=SR), frame_size=1000), fft_size=1024,
                                      circular_shift=True)
+
+
+@pytest.mark.parametrize("frame_size,dtype", [(1024, "f32"), (2048, "i16"), (4096, "f32"), (8192, "f32")])
+def test_include_nyquist(b2, frame_size, dtype):
+    """madmom stft(include_nyquist=True): frame_size/2 + 1 bins, the last one the (real) Nyquist bin; every other
+    bin is bitwise what the plain call gives.  Holds for the magnitude, log and difference stages on raw bins;
+    a filterbank takes frame_size/2 bins and refuses."""
+    from audio_tabs_b200.synth import synth_guitar
+    x = synth_guitar(3990 + frame_size, 0.6)
+    x = x + 0.2 * np.cos(np.pi * np.arange(len(x))).astype(np.float32)     # energy AT the Nyquist frequency
+    if dtype == "i16":
+        x = np.clip(np.round(x * 20000), -32768, 32767).astype(np.int16)
+
+    def stft_of(m, **kw):
+        return m.ShortTimeFourierTransform(m.FramedSignal(m.Signal(x, sample_rate=SR), frame_size=frame_size), **kw)
+    want = stft_of(ref, include_nyquist=True)
+    ours = stft_of(b2, include_nyquist=True)
+    got = np.asarray(ours)
+    N = frame_size // 2
+    assert got.shape == want.data.shape == (len(ours), N + 1) and ours.num_bins == N + 1
+    np.testing.assert_allclose(ours.bin_frequencies, want.bin_frequencies)
+    assert_stft_close(got, want.data)
+    assert np.abs(got[:, N]).max() > 10 * np.abs(got[:, N - 8:N - 2]).mean() and np.all(got[:, N].imag == 0)
+    assert np.array_equal(got[:, :N], np.asarray(stft_of(b2)))
+    circ = np.asarray(stft_of(b2, include_nyquist=True, circular_shift=True))
+    assert_stft_close(circ, stft_of(ref, include_nyquist=True, circular_shift=True).data)
+    spec = np.asarray(b2.Spectrogram(ours))
+    assert spec.shape == (len(ours), N + 1)
+    assert_close(spec, np.abs(want.data), rtol=1e-4, atol=1e-4 * np.abs(want.data).max(), what="magnitudes with Nyquist")
+    log = np.asarray(b2.LogarithmicSpectrogram(b2.Spectrogram(ours), mul=1, add=1))
+    # raw bins (no band sums): a bin far below the frame's peak carries the FFT's absolute rounding noise, 1e-4 max|X|
+    # at most (the magnitude bound above); d/dm log10(1 + m) <= 0.4343
+    tol = max(2e-5, 0.4343e-4 * float(np.abs(want.data).max()))
+    assert_close(log, np.log10(np.abs(want.data).astype(np.float32) + 1), rtol=1e-4, atol=tol, what="log with Nyquist")
+    d = np.asarray(b2.SpectrogramDifference(b2.LogarithmicSpectrogram(b2.Spectrogram(ours), mul=1, add=1), diff_frames=1,
+                                            positive_diffs=True))
+    assert d.shape == (len(ours), N + 1)
+    assert_close(d, ref.spectrogram_difference(log, 1, positive_diffs=True), atol=2e-5, what="diff with Nyquist")   # of OUR log rows
+    with pytest.raises(ValueError, match="include_nyquist"):
+        np.asarray(b2.FilteredSpectrogram(b2.Spectrogram(ours), num_bands=12))
 
 
 @pytest.mark.parametrize("seed", list(range(24)))

@@ -163,3 +163,26 @@ def test_context_stack_matches_oracle():
     from audio_tabs_b200.audio.chroma import context_stack
     spec = np.random.default_rng(0).standard_normal((20, 7)).astype(np.float32)
     np.testing.assert_array_equal(context_stack(spec, 15), ref.dcp_context(spec, 15))
+
+
+def test_oracle_online_difference_equals_the_offline_one_row_by_row():
+    """madmom's online mode (reset=False, BufferProcessor): feeding a spectrogram one row at a time gives, as the
+    last row of every call, the row the offline difference has at that position."""
+    from oracle import madmom_ref as ref
+    rng = np.random.default_rng(5)
+    L = rng.random((40, 9)).astype(np.float32)
+    for k, max_bins, positive in [(1, None, True), (3, None, False), (2, 3, True)]:
+        want = ref.spectrogram_difference(L, k, max_bins, positive)
+        proc = ref.SpectrogramDifferenceProcessor(diff_frames=k, diff_max_bins=max_bins, positive_diffs=positive)
+        first = proc(ref._Spec(L[:5]), reset=True)
+        np.testing.assert_array_equal(first.data, want[:5])
+        for t in range(5, 40):
+            out = proc(ref._Spec(L[t:t + 1]), reset=False)
+            assert out.data.shape == (5, 9)
+            np.testing.assert_array_equal(out.data[-1], want[t])
+        stacked = ref.SpectrogramDifferenceProcessor(diff_frames=k, positive_diffs=True, stack_diffs=np.hstack)
+        a = stacked(ref._Spec(L[:6]), reset=True)
+        b = stacked(ref._Spec(L[6:9]), reset=False)
+        assert a.shape == b.shape == (6, 18)
+        np.testing.assert_array_equal(b[:, :9], L[3:9])
+        np.testing.assert_array_equal(b[-3:, 9:], ref.spectrogram_difference(L, k, None, True)[6:9])
