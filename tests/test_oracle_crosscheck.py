@@ -172,6 +172,33 @@ def test_committed_goldens_against_the_second_statement():
 
 
 # ---- the librosa restatement (N3 row) against a third-party port of the same functions -------------------------------
+@pytest.mark.parametrize("frame_size,hop,dtype", [(1024, 441, "f32"), (2048, 441, "f32"), (4096, 441, "i16"), (8192, 4410, "f32"),
+                                                  (2048, 512, "f32")])
+def test_stft_against_scipy_signal_stft(frame_size, hop, dtype):
+    """EXTERNAL second opinion on madmom's framing + window + transform: scipy.signal.stft with boundary='zeros'
+    centres frame n on sample n * hop over zero padding, exactly FramedSignal's origin 0 -- a third-party
+    implementation of the same definition, not written for this repo.  (scipy divides by the window sum, and an
+    int16 signal enters madmom's transform through a window divided by 32767.)"""
+    import scipy.signal as ss
+    x = synth_guitar(1200 + frame_size, 1.37)
+    if dtype == "i16":
+        x = np.clip(np.round(x * 25000), -32768, 32767).astype(np.int16)
+    st = ref.ShortTimeFourierTransform(ref.FramedSignal(ref.Signal(x, sample_rate=44100), frame_size=frame_size, hop_size=hop))
+    w = np.hanning(frame_size)
+    xs = x.astype(np.float64) / (32767.0 if dtype == "i16" else 1.0)
+    _, _, Z = ss.stft(xs, fs=44100, window=w, nperseg=frame_size, noverlap=frame_size - hop, boundary="zeros", padded=True,
+                      return_onesided=True, scaling="spectrum")
+    Z = Z.T * w.sum()
+    T = st.data.shape[0]
+    assert T == int(np.ceil(len(x) / hop)) and Z.shape[0] >= T
+    err = np.abs(st.data - Z[:T, :frame_size // 2]).max()
+    assert err <= 2.5e-7 * np.abs(Z).max(), (err, np.abs(Z).max())       # complex64 storage of the oracle's float64 transform
+    # with the Nyquist bin
+    sn = ref.ShortTimeFourierTransform(ref.FramedSignal(ref.Signal(x, sample_rate=44100), frame_size=frame_size, hop_size=hop),
+                                       include_nyquist=True)
+    assert np.abs(sn.data - Z[:T]).max() <= 2.5e-7 * np.abs(Z).max()
+
+
 def test_librosa_restatement_against_transformers_audio_utils():
     """oracle/librosa_ref.py (Slaney mel filterbank, centred zero-padded periodic-Hann STFT, power mel spectrogram,
     power_to_db) against `transformers.audio_utils` -- an independent numpy port of the same librosa functions that
