@@ -127,12 +127,14 @@ namespace {
 template <class T>
 int upload(b200spec_plan *pl, const T *host, size_t n, T **out) {
   *out = nullptr;
-  const size_t alloc_n = n == 0 ? 1 : n;  // keep pointers valid
+  // every table is padded with zeros to a multiple of 16 bytes: the kernels stage them with 16-byte-granular bulk
+  // copies (bulk_stage.cuh); n == 0 still yields a valid pointer
+  const size_t bytes = ((n == 0 ? 1 : n) * sizeof(T) + 15) & ~size_t(15);
   void *d = nullptr;
-  CU_CHECK(cudaMalloc(&d, alloc_n * sizeof(T)));
+  CU_CHECK(cudaMalloc(&d, bytes));
   pl->allocs.push_back(d);
-  if (host && n > 0) CU_CHECK(cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice));
-  else CU_CHECK(cudaMemset(d, 0, alloc_n * sizeof(T)));   // nothing is read from a zero-length host array
+  CU_CHECK(cudaMemset(d, 0, bytes));
+  if (host && n > 0) CU_CHECK(cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice));   // nothing is read from a zero-length host array
   *out = reinterpret_cast<T *>(d);
   return 0;
 }

@@ -17,7 +17,7 @@ struct GroupsPerCta {
   static constexpr int fallback = (F == 8192) ? 2 : B2_GROUPS;    // short (band-limited filterbank), else two
 };
 
-constexpr size_t kMaxSmemPerCta = 227 * 1024;   // opt-in dynamic shared memory per CTA on sm_100
+constexpr size_t kMaxSmemPerCta = 227 * 1024 - kStaticSmemBytes;   // opt-in dynamic shared memory per CTA on sm_100, less the kernels' static words
 
 struct LaunchResult {
   cudaError_t err;
@@ -66,11 +66,7 @@ static cudaError_t launch_front_size(int in, int mode, FrontParams &p, int num_s
 template <int F>
 struct PairGroupsPerCta {
 #ifndef B2_PAIR_GROUPS_4096
-#ifdef B2_PAIR_INPLACE
-#define B2_PAIR_GROUPS_4096 4     // magnitudes in place of the consumed FFT columns (PairCfg::INPLACE)
-#else
-#define B2_PAIR_GROUPS_4096 3
-#endif
+#define B2_PAIR_GROUPS_4096 3     // 33 KB FFT buffer + 16.5 KB magnitudes per group: shared memory is full at three
 #endif
 #ifndef B2_PAIR_GROUPS_1024
 #define B2_PAIR_GROUPS_1024 5     // 96 registers per thread, no spills: measured 2.14 ms against 2.26 ms with four groups

@@ -20,6 +20,7 @@
 
 #include <type_traits>
 
+#include "bulk_stage.cuh"
 #include "fb_core.cuh"
 #include "fft_core.cuh"
 
@@ -417,15 +418,20 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
   int4 *s_band = reinterpret_cast<int4 *>(smem + p.o_band);
   float *s_dw = reinterpret_cast<float *>(smem + p.o_dw);
 
-  for (int i = threadIdx.x; i < F; i += blockDim.x) s_win[i] = p.window[i];
-  for (int i = threadIdx.x; i < C::TW3; i += blockDim.x) s_tw3[i] = p.tw3[i];
-  for (int i = threadIdx.x; i < C::PT; i += blockDim.x) s_pt[i] = p.pt[i];
-  for (int i = threadIdx.x; i < C::WR; i += blockDim.x) s_wr[i] = p.wr[i];
+  // plan tables: bulk copies by the TMA unit (bulk_stage.cuh), in flight while the work buffers are cleared
+  __shared__ __align__(8) uint64_t s_stage_bar;
+  bulk_stage_begin(&s_stage_bar, [&](auto &&table) {
+    table(s_win, p.window, (uint32_t)sizeof(float) * F);
+    table(s_tw3, p.tw3, (uint32_t)sizeof(float2) * C::TW3);
+    table(s_pt, p.pt, (uint32_t)sizeof(float2) * C::PT);
+    table(s_wr, p.wr, (uint32_t)sizeof(float2) * C::WR);
+    if (MODE == MODE_LOGFILT) {
+      if (!p.fb_w4_global) table(s_w4, p.fb_w4, (uint32_t)sizeof(float4) * p.fb_ns * p.fb_L * kGroupThreads);
+      table(s_band, p.fb_band, (uint32_t)sizeof(int4) * p.num_bands);
+      table(s_dw, p.fb_dw, (uint32_t)sizeof(float) * p.fb_ndw);
+    }
+  });
   if (MODE == MODE_LOGFILT) {
-    if (!p.fb_w4_global)
-      for (int i = threadIdx.x; i < p.fb_ns * p.fb_L * kGroupThreads; i += blockDim.x) s_w4[i] = p.fb_w4[i];
-    for (int i = threadIdx.x; i < p.num_bands; i += blockDim.x) s_band[i] = p.fb_band[i];
-    for (int i = threadIdx.x; i < p.fb_ndw; i += blockDim.x) s_dw[i] = p.fb_dw[i];
     TailCtx::stage_proj(p, smem);
     // magnitudes (and their padding, which zero-weight taps may read) start out finite
     float *allmags = reinterpret_cast<float *>(smem + p.o_groups);
@@ -433,7 +439,7 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
       for (int i = threadIdx.x; i < (TB > 1 ? TB * MS : p.mag_cap); i += blockDim.x)
         reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(allmags) + (size_t)gi * p.group_bytes + p.g_mags)[i] = 0.f;
   }
-  __syncthreads();
+  bulk_stage_wait(&s_stage_bar);
 
   // Warp w of every group lands on scheduler (SMSP) w.  Roles inside a group are not uniform (the
   // self-paired columns run on virtual warp 0, the band stage uses the low warps), so the virtual

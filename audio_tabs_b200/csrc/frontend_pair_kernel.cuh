@@ -144,26 +144,16 @@ inline size_t multi_smem_layout(MultiParams &m, int G) {
 
 #if defined(__CUDACC__)
 
-// copies one resolution's tables into shared memory (all threads of the CTA; the caller syncs afterwards)
-template <int F>
-__device__ __forceinline__ void pair_stage_tables(const FrontParams &p, unsigned char *smem) {
+// one resolution's tables for bulk_stage_begin: table(dst in shared memory, src in global memory, bytes)
+template <int F, class Table>
+__device__ __forceinline__ void pair_tables(const FrontParams &p, unsigned char *smem, Table &&table) {
   using C2 = FftCfg<2 * F>;
-  if (p.o_win >= 0) {
-    float *s_win = reinterpret_cast<float *>(smem + p.o_win);
-    for (int i = threadIdx.x; i < F; i += blockDim.x) s_win[i] = p.window[i];
-  }
-  float2 *s_tw3 = reinterpret_cast<float2 *>(smem + p.o_tw3);
-  float2 *s_wr = reinterpret_cast<float2 *>(smem + p.o_wr);
-  float4 *s_w4 = reinterpret_cast<float4 *>(smem + p.o_w4);
-  int4 *s_band = reinterpret_cast<int4 *>(smem + p.o_band);
-  float *s_dw = reinterpret_cast<float *>(smem + p.o_dw);
-  for (int i = threadIdx.x; i < C2::TW3C; i += blockDim.x) s_tw3[i] = p.tw3[i];   // F-point tables (pair_tw3 / pair_wr)
-  for (int i = threadIdx.x; i < C2::WR; i += blockDim.x) s_wr[i] = p.wr[i];
-  if (!p.fb_w4_global)
-    for (int i = threadIdx.x; i < p.fb_ns * p.fb_L * kGroupThreads; i += blockDim.x) s_w4[i] = p.fb_w4[i];
-  for (int i = threadIdx.x; i < p.num_bands; i += blockDim.x) s_band[i] = p.fb_band[i];
-  for (int i = threadIdx.x; i < p.fb_ndw; i += blockDim.x) s_dw[i] = p.fb_dw[i];
-  TailCtx::stage_proj(p, smem);
+  if (p.o_win >= 0) table(smem + p.o_win, p.window, (uint32_t)sizeof(float) * F);
+  table(smem + p.o_tw3, p.tw3, (uint32_t)sizeof(float2) * C2::TW3C);   // F-point tables (pair_tw3 / pair_wr)
+  table(smem + p.o_wr, p.wr, (uint32_t)sizeof(float2) * C2::WR);
+  if (!p.fb_w4_global) table(smem + p.o_w4, p.fb_w4, (uint32_t)sizeof(float4) * p.fb_ns * p.fb_L * kGroupThreads);
+  table(smem + p.o_band, p.fb_band, (uint32_t)sizeof(int4) * p.num_bands);
+  table(smem + p.o_dw, p.fb_dw, (uint32_t)sizeof(float) * p.fb_ndw);
 }
 
 // One task -- frames [f0, f1) of clip c -- of one resolution, run by the 128 threads of group g.
@@ -335,11 +325,13 @@ template <int F, int IN, int G>
 __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front_pair(const FrontParams p) {
   using P = PairCfg<F>;
   extern __shared__ __align__(16) unsigned char smem[];
-  pair_stage_tables<F>(p, smem);
+  __shared__ __align__(8) uint64_t s_stage_bar;     // plan tables arrive by TMA bulk copies (bulk_stage.cuh)
+  bulk_stage_begin(&s_stage_bar, [&](auto &&table) { pair_tables<F>(p, smem, table); });
+  TailCtx::stage_proj(p, smem);
   for (int gi = 0; gi < G; ++gi)      // magnitudes (and their padding, which zero-weight taps may read) start out finite
     for (int i = threadIdx.x; i < P::TB * P::MS; i += blockDim.x)
       reinterpret_cast<float *>(smem + p.o_groups + (size_t)gi * p.group_bytes + p.g_mags)[i] = 0.f;
-  __syncthreads();
+  bulk_stage_wait(&s_stage_bar);
 
   // virtual warp roles rotated by the group number (see k_front)
   const int g = threadIdx.x / kGroupThreads;
@@ -367,16 +359,20 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front_pair(const FrontP
 template <int IN, int G>
 __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front_multi(const MultiParams m) {
   extern __shared__ __align__(16) unsigned char smem[];
-  for (int i = 0; i < m.n_res; ++i) {
-    const FrontParams &p = m.r[i];
-    if (p.frame_size == 1024) pair_stage_tables<1024>(p, smem);
-    else if (p.frame_size == 2048) pair_stage_tables<2048>(p, smem);
-    else pair_stage_tables<4096>(p, smem);
-  }
+  __shared__ __align__(8) uint64_t s_stage_bar;     // every resolution's tables arrive by TMA bulk copies, one barrier
+  bulk_stage_begin(&s_stage_bar, [&](auto &&table) {
+    for (int i = 0; i < m.n_res; ++i) {
+      const FrontParams &p = m.r[i];
+      if (p.frame_size == 1024) pair_tables<1024>(p, smem, table);
+      else if (p.frame_size == 2048) pair_tables<2048>(p, smem, table);
+      else pair_tables<4096>(p, smem, table);
+    }
+  });
+  for (int i = 0; i < m.n_res; ++i) TailCtx::stage_proj(m.r[i], smem);
   const FrontParams &p0 = m.r[0];
   for (int i = threadIdx.x; i < (p0.group_bytes * G) / 4; i += blockDim.x)     // every group block starts out zero (finite)
     reinterpret_cast<float *>(smem + p0.o_groups)[i] = 0.f;
-  __syncthreads();
+  bulk_stage_wait(&s_stage_bar);
 
   const int g = threadIdx.x / kGroupThreads;
   const int tid = ((((threadIdx.x >> 5) + g) & 3) << 5) | (threadIdx.x & 31);

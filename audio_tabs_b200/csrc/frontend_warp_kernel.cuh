@@ -140,13 +140,16 @@ __global__ void __launch_bounds__(32 * NW, 1) k_front_warp(const FrontParams p) 
   float4 *s_w4 = reinterpret_cast<float4 *>(smem + p.o_w4);
   int4 *s_band = reinterpret_cast<int4 *>(smem + p.o_band);
   float *s_dw = reinterpret_cast<float *>(smem + p.o_dw);
-  for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) s_tw[i] = p.tw3[i];
-  for (int i = threadIdx.x; i < p.fb_ns * p.fb_L * 32; i += blockDim.x) s_w4[i] = p.fb_w4[i];
-  for (int i = threadIdx.x; i < p.num_bands; i += blockDim.x) s_band[i] = p.fb_band[i];
-  for (int i = threadIdx.x; i < p.fb_ndw; i += blockDim.x) s_dw[i] = p.fb_dw[i];
+  __shared__ __align__(8) uint64_t s_stage_bar;     // plan tables arrive by TMA bulk copies (bulk_stage.cuh)
+  bulk_stage_begin(&s_stage_bar, [&](auto &&table) {
+    table(s_tw, p.tw3, (uint32_t)sizeof(float2) * 32 * 32);
+    table(s_w4, p.fb_w4, (uint32_t)sizeof(float4) * p.fb_ns * p.fb_L * 32);
+    table(s_band, p.fb_band, (uint32_t)sizeof(int4) * p.num_bands);
+    table(s_dw, p.fb_dw, (uint32_t)sizeof(float) * p.fb_ndw);
+  });
   for (int i = threadIdx.x; i < (p.group_bytes * NW) / 4; i += blockDim.x)      // every warp block starts out zero (finite)
     reinterpret_cast<float *>(smem + p.o_groups)[i] = 0.f;
-  __syncthreads();
+  bulk_stage_wait(&s_stage_bar);
 
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char *wmem = smem + p.o_groups + (size_t)wid * p.group_bytes;
