@@ -307,6 +307,47 @@ __global__ void k_filter_log(const float *__restrict__ spec, long long ld_spec, 
   }
 }
 
+// The fused kernels run without warm-up rows (FrontParams::seam_fix): the first kd rows of every task but a clip's
+// first were differenced against a stale ring.  One warp per such row rewrites the difference (and the flux) from
+// the (log-)filtered rows L, which are complete in global memory by now: D[r] = L[r] - L[r - kd].
+// Tasks: task_off / chunk as k_setup_tasks left them; task i of clip c starts at frame (i - task_off[c]) * chunk.
+__global__ void k_seam_diff(const int *__restrict__ task_off, int n_clips, int chunk, const long long *__restrict__ frame_off,
+                            const float *__restrict__ L, long long ld_L, int B, int kd, int positive,
+                            float *__restrict__ out_diff, long long ld_out, float *__restrict__ flux) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int kfix = min(kd, chunk);                       // rows of a task whose lagged row belongs to another task
+  const long long total = (long long)task_off[n_clips] * kfix;
+  for (long long idx = warp; idx < total; idx += nwarps) {
+    const int task = (int)(idx / kfix), t = (int)(idx - (long long)task * kfix);
+    int lo = 0, hi = n_clips;
+    while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (task_off[mid] <= task) lo = mid; else hi = mid;
+    }
+    const int f0 = (task - task_off[lo]) * chunk;
+    if (f0 == 0) continue;                               // a clip's first task: rows < kd are 0, written by the fused kernel
+    const long long row0 = frame_off[lo];
+    const int f = f0 + t;
+    if (f >= (int)(frame_off[lo + 1] - row0)) continue;
+    const long long r = row0 + f;
+    const float *x = L + r * ld_L, *ref = L + (r - kd) * ld_L;
+    float fsum = 0.f;
+    for (int j = lane; j < B; j += 32) {
+      float D = f >= kd ? x[j] - ref[j] : 0.f;
+      if (positive) D = fmaxf(D, 0.f);
+      if (out_diff != nullptr) out_diff[r * ld_out + j] = D;
+      fsum += D;
+    }
+    if (flux != nullptr) {
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) fsum += __shfl_xor_sync(0xffffffffu, fsum, d);
+      if (lane == 0) flux[r] = fsum;
+    }
+  }
+}
+
 // one warp per row: lagged (positive) difference inside each clip, flux row sum, projection
 __global__ void k_diff_flux_proj(const float *__restrict__ L, long long ld_L, const long long *__restrict__ frame_off,
                                  int n_clips, long long rows, int B, int kd, int positive, int max_bins, int num_classes,

@@ -374,17 +374,35 @@ int carve_workspace(void *ws, size_t bytes, int n_clips, Workspace &w) {
   return 0;
 }
 
-int choose_chunk(const b200spec_plan *pl, int F, long long total_frames, int kd) {
-  const int G = (F == 8192) ? 3 : (F <= 2048) ? 8 : 4;   // frames 1024 / 2048: 16 warps per SM pull tasks of their own
-  const long long slots = (long long)pl->num_sms * G;
-  long long chunk = total_frames / (slots * 8);
-  const int lo = F <= 2048 ? (kd > 0 ? 8 : 2) : (kd > 0 ? 16 : 4);   // smallest task (a warp runs its frames one after the other)
-  if (chunk < lo) chunk = lo;
-  if (chunk > 96) chunk = 96;     // measured on B200: 64-96 frames per task balance warm-up rows and tail imbalance
-  if (F <= 2048 && chunk > 48) chunk = 48;   // 2368 warps pull tasks there: ten tasks each instead of five
-  // a task transforms chunk + kd frames (kd warm-up rows of the difference); keep that a multiple of the
-  // tail batch (4 frames, pairs of frames in k_front_pair) so no step runs half empty
-  if (chunk >= 16) chunk -= (chunk + kd) % 4;
+// Frames per task.  Tasks are pulled from one counter by W workers per GPU (warps of the warp kernels, groups of the
+// others), all of about the same length, so the kernel runs ceil(tasks / W) rounds of (chunk + warm-up rows + a
+// per-task overhead) frames: a chunk that leaves the last round nearly empty wastes up to a whole round (measured on
+// B200, 64 x 18000 frames at frame 1024: 48-frame tasks = 10.15 rounds run 1.409 ms, 16- or 64-frame tasks 1.378 ms,
+// 96-frame tasks = 5.08 rounds 1.486 ms).  The candidate with the smallest modelled cost wins; a small batch
+// (less than one round) gets the smallest tasks so that every SM has work.
+// kd: warm-up rows per task (0 when the seam fix-up forms the first differences, see launch_front).
+// per_sm: workers resident per SM (16 warps of the warp kernel, 2-5 groups of the others); overhead: task fetch and
+// the cold L1 of a task's first frames, in frames (0.75 for a warp, 1 for a group: fitted to the measured sweeps).
+int choose_chunk(const b200spec_plan *pl, int per_sm, double overhead, long long total_frames, int n_clips, int kd) {
+  const double workers = (double)pl->num_sms * per_sm;
+  const double clips = n_clips > 0 ? (double)n_clips : 1.0;
+  const double per_clip = (double)total_frames / clips;
+  static const int cand[] = {2, 4, 8, 12, 16, 20, 24, 28, 32, 40, 48, 56, 64, 72, 80, 96};
+  int best = 16;
+  double best_cost = 1e300;
+  for (int c0 : cand) {
+    int c = c0;
+    if (c >= 16) c -= (c + kd) % 4;            // a task transforms c + kd frames: whole tail batches (4 frames / pairs)
+    else if ((c + kd) & 1) c += 1;             // whole pairs of frames
+    const double tasks = clips * std::ceil(per_clip / c);
+    const double rounds = std::max(1.0, std::ceil(tasks / workers));
+    const double cost = rounds * (c + kd + overhead);
+    if (cost < best_cost * (1.0 - 1e-9) || (cost <= best_cost * (1.0 + 1e-9) && c > best)) {   // ties: fewer, longer tasks
+      best_cost = cost;
+      best = c;
+    }
+  }
+  long long chunk = best;
 #ifdef B200SPEC_TUNING
   if (const char *e = getenv("B200SPEC_CHUNK")) {   // tuning override
     const int v = atoi(e);
@@ -461,7 +479,42 @@ int launch_front(const b200spec_plan *pl, int res, int mode, const void *d_sig, 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   NvtxRange range(range_name(mode, r.frame_size));
 
-  const int chunk = choose_chunk(pl, r.frame_size, total_frames, mode == b2::MODE_LOGFILT ? r.diff_frames : 0);
+  // The log-filtered path of frames <= 4096 runs the pair kernel (two frames per complex FFT); a configuration
+  // whose tables do not fit next to the larger FFT buffer keeps the one-frame kernel (as does B200SPEC_PAIR=0 in a
+  // tuning build: A/B measurements).
+#ifdef B200SPEC_TUNING
+  static const bool use_pair = []() { const char *v = getenv("B200SPEC_PAIR"); return !(v && v[0] == '0'); }();
+#else
+  constexpr bool use_pair = true;
+#endif
+#ifdef B2_NO_WARP      // tuning: keep the pair kernel at frames 1024 / 2048
+  constexpr bool use_warp = false;
+#else
+  constexpr bool use_warp = true;
+#endif
+#ifndef B2_WARP_MAX_F  // tuning: -DB2_WARP_MAX_F=1024 keeps the pair kernel at frame 2048
+#define B2_WARP_MAX_F 2048
+#endif
+  // Lagged difference without warm-up rows: a task transforms its own frames only, and the first diff_frames rows of
+  // every task -- differenced against a ring that another task left behind -- are rewritten by k_seam_diff from
+  // the filtered rows once they are all in global memory (1-2 transforms less per task, and tasks can be as small
+  // as the load balance asks for: config 2 on B200 11.45 -> 11.33 ms at equal task sizes).  Needs the filtered rows in the
+  // output matrix; a flux-only call keeps the warm-up rows.  No difference wanted: no warm-up either.
+  const bool want_diff = mode == b2::MODE_LOGFILT && r.diff_frames > 0 && (p.col_diff >= 0 || p.flux != nullptr);
+#ifdef B200SPEC_TUNING   // A/B knob of tuning builds: B200SPEC_SEAM=0 keeps the warm-up rows
+  static const bool seam_on = []() { const char *v = getenv("B200SPEC_SEAM"); return !(v && v[0] == '0'); }();
+#else
+  constexpr bool seam_on = true;
+#endif
+  const bool seam_fix = seam_on && mode == b2::MODE_LOGFILT && r.diff_frames > 0 &&
+                        (!want_diff || (p.out != nullptr && p.col_spec >= 0));
+  const bool warp_path = use_warp && use_pair && mode == b2::MODE_LOGFILT && (r.frame_size == 1024 || r.frame_size == B2_WARP_MAX_F) &&
+                         r.d_w32_tw != nullptr && p.proj == nullptr && (r.frame_size == 1024 || r.w32_ns * r.w32_L <= 30);
+  const int per_sm = warp_path ? 16 : r.frame_size == 1024 ? 5 : r.frame_size == 2048 ? 4 : 3;
+  const double task_overhead = warp_path ? 0.75 : 1.0;   // fitted to the task-size sweeps in profiles/r02_variants.txt
+  const int chunk = choose_chunk(pl, per_sm, task_overhead, total_frames, n_clips,
+                                 (mode == b2::MODE_LOGFILT && !seam_fix) ? r.diff_frames : 0);
+  p.seam_fix = seam_fix ? 1 : 0;
   b2::k_setup_tasks<<<1, 1024, 0, st>>>(reinterpret_cast<const long long *>(d_frame_off), n_clips, chunk,
                                          w.task_off, w.counter);
   CU_CHECK(cudaGetLastError());
@@ -479,28 +532,23 @@ int launch_front(const b200spec_plan *pl, int res, int mode, const void *d_sig, 
   const int in = (pl->dtype == B200SPEC_I16 ? 2 : 0) + (pl->channels == 2 ? 1 : 0);
   const long long task_bound = total_frames / chunk + n_clips;
   cudaError_t e;
-  // The log-filtered path of frames <= 4096 runs the pair kernel (two frames per complex FFT); a configuration
-  // whose tables do not fit next to the larger FFT buffer keeps the one-frame kernel (as does B200SPEC_PAIR=0 in a
-  // tuning build: A/B measurements).
-#ifdef B200SPEC_TUNING
-  static const bool use_pair = []() { const char *v = getenv("B200SPEC_PAIR"); return !(v && v[0] == '0'); }();
-#else
-  constexpr bool use_pair = true;
-#endif
-#ifdef B2_NO_WARP      // tuning: keep the pair kernel at frames 1024 / 2048
-  constexpr bool use_warp = false;
-#else
-  constexpr bool use_warp = true;
-#endif
-#ifndef B2_WARP_MAX_F  // tuning: -DB2_WARP_MAX_F=1024 keeps the pair kernel at frame 2048
-#define B2_WARP_MAX_F 2048
-#endif
+  auto seam_fixup = [&]() -> int {
+    if (!(seam_fix && want_diff)) return 0;
+    long long warps = task_bound * std::min(r.diff_frames, chunk);
+    long long blocks = (warps + 7) / 8;
+    if (blocks > pl->num_sms * 8) blocks = pl->num_sms * 8;
+    b2::k_seam_diff<<<(int)(blocks < 1 ? 1 : blocks), 256, 0, st>>>(
+        w.task_off, n_clips, chunk, p.frame_off, p.out + p.col_spec, p.ld_out, r.num_bands, r.diff_frames, r.positive,
+        p.col_diff >= 0 ? p.out + p.col_diff : nullptr, p.ld_out, p.flux);
+    CU_CHECK(cudaGetLastError());
+    g_launches++;
+    return 0;
+  };
   // frames 1024 / 2048: one warp per FFT (frontend_warp_kernel.cuh); the projection output keeps the pair kernel
   // (frame 2048 runs one frame per FFT there and walks the filterbank once per frame: with a filterbank that covers the
   //  whole spectrum -- librosa's 128 mel bands: 45 bins per lane -- the pair kernel, which amortises the weights over
   //  four frames, is the faster one: 15.7 against 18.6 ms on the onset-strength workload)
-  if (use_warp && use_pair && mode == b2::MODE_LOGFILT && (r.frame_size == 1024 || r.frame_size == B2_WARP_MAX_F) &&
-      r.d_w32_tw != nullptr && p.proj == nullptr && (r.frame_size == 1024 || r.w32_ns * r.w32_L <= 30)) {
+  if (warp_path) {
     b2::FrontParams q = p;
     q.tw3 = r.d_w32_tw;
     q.fb_w4 = r.d_w32_w4;
@@ -514,7 +562,7 @@ int launch_front(const b200spec_plan *pl, int res, int mode, const void *d_sig, 
                              : b2_launch_warp_2048(in, q, pl->num_sms, task_bound, st);
     if (e == cudaSuccess) {
       g_launches++;
-      return 0;
+      return seam_fixup();
     }
     if (e != cudaErrorInvalidConfiguration)
       return fail(B200SPEC_ERR_CUDA, "front-end (warp) kernel launch failed: %s", cudaGetErrorString(e));
@@ -531,7 +579,7 @@ int launch_front(const b200spec_plan *pl, int res, int mode, const void *d_sig, 
     }
     if (e == cudaSuccess) {
       g_launches++;
-      return 0;
+      return seam_fixup();
     }
     if (e != cudaErrorInvalidConfiguration)
       return fail(B200SPEC_ERR_CUDA, "front-end (pair) kernel launch failed: %s", cudaGetErrorString(e));
@@ -548,7 +596,7 @@ int launch_front(const b200spec_plan *pl, int res, int mode, const void *d_sig, 
                 "shared memory than an SM has; use the unfused stft / filter_log calls", r.frame_size, r.num_bands);
   if (e != cudaSuccess) return fail(B200SPEC_ERR_CUDA, "front-end kernel launch failed: %s", cudaGetErrorString(e));
   g_launches++;
-  return 0;
+  return seam_fixup();
 }
 
 void fill_out_params(const b200spec_out_desc &out, const ResPlan &r, b2::FrontParams &p) {

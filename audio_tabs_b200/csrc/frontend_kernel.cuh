@@ -87,6 +87,10 @@ struct FrontParams {
   // outputs (MODE_SPECTRUM)
   float *spec_out;      // (rows, spec_ld) float or float2
   int spec_ld;          // N, or N + 1 with the Nyquist bin (madmom include_nyquist)
+  // 1: a task transforms its own frames only -- no warm-up rows for the lagged difference.  The first diff_frames
+  // rows of every task (but a clip's first) then hold a difference against a stale ring; k_seam_diff rewrites them
+  // from the (log-)filtered rows in global memory once the kernel is done (b200spec.cu: launch_front).
+  int seam_fix;
   int spec_complex;
   int circular_shift;   // madmom stft(circular_shift=True) with fft_size == frame_size: the two halves of the windowed
                         // frame are swapped before the transform = bin k times (-1)^k (magnitudes are unchanged)
@@ -500,7 +504,7 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
     const int T = (int)(p.frame_off[c + 1] - row0);
     const int f0 = (task - p.task_off[c]) * p.chunk;
     const int f1 = min(T, f0 + p.chunk);
-    const int fs = (MODE == MODE_LOGFILT && kd > 0) ? max(0, f0 - kd) : f0;  // warm-up rows for the diff
+    const int fs = (MODE == MODE_LOGFILT && kd > 0 && !p.seam_fix) ? max(0, f0 - kd) : f0;  // warm-up rows for the diff
     Samples<IN> S{clip_base<IN>(p.sig, samp0)};
     float cscale = (MODE == MODE_LOGFILT && p.clip_scale != nullptr) ? __ldg(p.clip_scale + c) : 1.f;
     if (p.power) cscale *= cscale;       // |g x|^2 = g^2 |x|^2: a power spectrogram scales with the gain squared

@@ -195,7 +195,7 @@ __device__ __forceinline__ void pair_run_task(const FrontParams &p, unsigned cha
   const long long samp0 = p.clip_off[c];
   const long long nsamp = p.clip_off[c + 1] - samp0;
   const long long row0 = p.frame_off[c];
-  const int fs = kd > 0 ? max(0, f0 - kd) : f0;              // warm-up rows for the difference
+  const int fs = (kd > 0 && !p.seam_fix) ? max(0, f0 - kd) : f0;     // warm-up rows for the difference
   Samples<IN> S{clip_base<IN>(p.sig, samp0)};
   float cscale = p.clip_scale != nullptr ? __ldg(p.clip_scale + c) : 1.f;
   if (p.power) cscale *= cscale;         // a power spectrogram scales with the gain squared
