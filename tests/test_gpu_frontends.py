@@ -364,6 +364,56 @@ def test_superflux_flux_only_batch(b2):
         o += t
 
 
+@pytest.mark.parametrize("frame_size", [1024, 2048, 4096, 8192])
+@pytest.mark.parametrize("lag", [1, 3, 7, 16])
+def test_difference_across_task_seams(b2, frame_size, lag):
+    """The fused kernels cut a clip into tasks and run them without warm-up rows; the first `lag` rows of every task
+    are rewritten by the seam kernel from the filtered rows.  Small batches get 2-frame tasks, so with lags up to
+    B200SPEC_MAX_DIFF_FRAMES every row is a seam row here; the flux must agree whether it comes with the stacked
+    matrix (seam path) or alone (warm-up rows: there is no matrix to read the lagged rows from)."""
+    import dataclasses
+    import torch
+    from audio_tabs_b200.frontends import log_filt_spec
+    from audio_tabs_b200.plan import FrontEnd
+    from audio_tabs_b200.synth import synth_guitar
+    spec = dataclasses.replace(log_filt_spec(frame_size, 441.0, 12, diff_ratio=0.5), diff_frames=lag, positive_diffs=True)
+    clips = [synth_guitar(3300 + 7 * i + lag, sec) for i, sec in enumerate((0.9, 0.011, 0.35, 2.2))]
+    fe = FrontEnd([spec], device=0)
+    packed = fe.pack(clips)
+    flux_with = torch.empty(packed.total_frames, dtype=torch.float32, device="cuda")
+    full = fe.run_packed(packed, flux=[flux_with])
+    flux_alone = torch.full((packed.total_frames,), -1.0, dtype=torch.float32, device="cuda")
+    fe.run_packed(packed, out=False, flux=[flux_alone])
+    B = spec.num_bands
+    o = 0
+    for c in clips:
+        t = ref.num_frames_for(len(c), 441.0)
+        L = ref.log_filtered_spectrogram(c, frame_size=frame_size, num_bands=12)
+        L = np.asarray(L.data if hasattr(L, "data") else L)
+        D = ref.spectrogram_difference(L, lag, positive_diffs=True) if t > lag else np.zeros_like(L)
+        assert_close(full[o:o + t, :B].cpu().numpy(), L.astype(np.float32), what="spec, lag %d" % lag)
+        assert_close(full[o:o + t, B:].cpu().numpy(), D.astype(np.float32), atol=2e-5, what="diff, lag %d" % lag)
+        o += t
+    want_flux = full[:, B:].sum(dim=1).cpu().numpy()
+    assert_close(flux_with.cpu().numpy(), want_flux, rtol=1e-5, atol=1e-5, what="flux next to the matrix")
+    assert_close(flux_alone.cpu().numpy(), want_flux, rtol=1e-4, atol=1e-4, what="flux alone")
+
+
+def test_rows_do_not_depend_on_the_batch(b2):
+    """Without warm-up rows every task starts on an even frame, so the two frames that share a complex FFT are
+    always (2i, 2i + 1) and the lagged difference is formed from the very values that are stored: a clip's rows are
+    bitwise the same whether it is processed alone or inside a large batch (different task sizes, different SMs)."""
+    from audio_tabs_b200.frontends import beat_specs
+    from audio_tabs_b200.plan import FrontEnd
+    from audio_tabs_b200.synth import synth_guitar
+    fe = FrontEnd(beat_specs(), device=0)
+    clip = synth_guitar(3400, 4.0)
+    alone = fe.process_batch([clip])[0]
+    crowd = [synth_guitar(3401 + i, 30.0) for i in range(12)]
+    batch = fe.process_batch(crowd[:5] + [clip] + crowd[5:])
+    assert np.array_equal(batch[5], alone)
+
+
 # ---- ingest: per-clip peak + fused peak normalisation (SURVEY §8f N4) ---------------------------
 @pytest.mark.parametrize("dtype,channels", [("f32", 1), ("f32", 2), ("i16", 1), ("i16", 2)])
 def test_clip_peak_and_fused_normalisation(b2, dtype, channels):
