@@ -508,7 +508,7 @@ def run_ours(args, rank, world, local_rank):
                 "peak_source": peak_src,
                 "kernel": ("k_front_multi (all three resolutions in one launch" if fe.one_launch else "k_front_pair<%d> (" % dom["frame_size"])
                 + "fused frame+FFT+filterbank+log+diff, two frames per complex FFT)",
-                "launches_per_step": "1 front-end kernel + 1 task-table kernel" if fe.one_launch else "3 front-end kernels + 3 task-table kernels",
+                "launches_per_step": "1 front-end kernel + 1 task-table kernel" if fe.one_launch else "3 front-end kernels + 3 task-table kernels + 3 seam kernels (first diff rows of every task; inside the per-kernel times)",
                 "kernel_ms": dom["ms"], "alg_bytes_per_launch": dom["alg_bytes"],
                 "fp32_tflops": dom["fp32_tflops"], "fp32_frac_of_74.5": dom["fp32_tflops"] / fp32_peak,
                 "note": "hop 441 makes the path FP32-issue bound (31-78 flop/B vs ridge 11); see DESIGN.md",
