@@ -186,6 +186,10 @@ int b200spec_spectrogram(const b200spec_plan *plan, int32_t res, const void *d_s
  * K1 + K2 + K3 fused: frames -> window -> FFT -> magnitude -> banded filterbank -> log10(mul*y+add)
  * -> lagged (positive) difference -> optional flux / projection, written straight into the
  * caller's stacked layout.  Replaces the whole madmom chain named above for resolution `res`.
+ * Launches on `stream`: a task table, the fused kernel and -- when a difference or flux is wanted and the filtered
+ * rows go to d_out (col_spec >= 0) -- a seam kernel that forms the first diff_frames difference rows of every task
+ * from the rows in d_out (the fused kernel then transforms no warm-up frames; without the filtered rows in d_out
+ * it does).  A clip's rows do not depend on the batch it is processed in (bitwise).
  */
 int b200spec_logfilt(const b200spec_plan *plan, int32_t res, const void *d_sig, const int64_t *d_clip_off,
                      const int64_t *d_frame_off, int32_t n_clips, int64_t total_frames,
