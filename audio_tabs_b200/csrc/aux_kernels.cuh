@@ -6,14 +6,19 @@
 namespace b2 {
 
 // ---- task table: tasks per clip = ceil(frames / chunk), exclusive prefix -> task_off -----------
-__global__ void k_setup_tasks(const long long *__restrict__ frame_off, int n_clips, int chunk,
+// The last tail_clips clips are cut into tasks of chunk_small frames (FrontParams::tail_clips; 0 = one size).
+__global__ void k_setup_tasks(const long long *__restrict__ frame_off, int n_clips, int chunk, int chunk_small, int tail_clips,
                               int *__restrict__ task_off, int *__restrict__ task_counter) {
   __shared__ int s_part[1024];
   const int t = threadIdx.x;
   const int per = (n_clips + 1023) / 1024;
   const int lo = min(t * per, n_clips), hi = min(lo + per, n_clips);
   int sum = 0;
-  for (int c = lo; c < hi; ++c) sum += (int)((frame_off[c + 1] - frame_off[c] + chunk - 1) / chunk);
+  auto tasks_of = [&](int c) {
+    const int ch = c >= n_clips - tail_clips ? chunk_small : chunk;
+    return (int)((frame_off[c + 1] - frame_off[c] + ch - 1) / ch);
+  };
+  for (int c = lo; c < hi; ++c) sum += tasks_of(c);
   s_part[t] = sum;
   __syncthreads();
   for (int d = 1; d < 1024; d <<= 1) {  // Hillis-Steele inclusive scan
@@ -25,7 +30,7 @@ __global__ void k_setup_tasks(const long long *__restrict__ frame_off, int n_cli
   int run = s_part[t] - sum;
   for (int c = lo; c < hi; ++c) {
     task_off[c] = run;
-    run += (int)((frame_off[c + 1] - frame_off[c] + chunk - 1) / chunk);
+    run += tasks_of(c);
   }
   if (t == 1023) task_off[n_clips] = s_part[1023];
   if (t == 0) *task_counter = 0;
@@ -311,22 +316,24 @@ __global__ void k_filter_log(const float *__restrict__ spec, long long ld_spec, 
 // first were differenced against a stale ring.  One warp per such row rewrites the difference (and the flux) from
 // the (log-)filtered rows L, which are complete in global memory by now: D[r] = L[r] - L[r - kd].
 // Tasks: task_off / chunk as k_setup_tasks left them; task i of clip c starts at frame (i - task_off[c]) * chunk.
-__global__ void k_seam_diff(const int *__restrict__ task_off, int n_clips, int chunk, const long long *__restrict__ frame_off,
+__global__ void k_seam_diff(const int *__restrict__ task_off, int n_clips, int chunk, int chunk_small, int tail_clips,
+                            const long long *__restrict__ frame_off,
                             const float *__restrict__ L, long long ld_L, int B, int kd, int positive,
                             float *__restrict__ out_diff, long long ld_out, float *__restrict__ flux) {
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  const int kfix = min(kd, chunk);                       // rows of a task whose lagged row belongs to another task
-  const long long total = (long long)task_off[n_clips] * kfix;
+  const long long total = (long long)task_off[n_clips] * kd;   // the first kd rows of a task have their lagged row in another task
   for (long long idx = warp; idx < total; idx += nwarps) {
-    const int task = (int)(idx / kfix), t = (int)(idx - (long long)task * kfix);
+    const int task = (int)(idx / kd), t = (int)(idx - (long long)task * kd);
     int lo = 0, hi = n_clips;
     while (hi - lo > 1) {
       int mid = (lo + hi) >> 1;
       if (task_off[mid] <= task) lo = mid; else hi = mid;
     }
-    const int f0 = (task - task_off[lo]) * chunk;
+    const int ch = lo >= n_clips - tail_clips ? chunk_small : chunk;
+    if (t >= ch) continue;                               // that row is the next task's
+    const int f0 = (task - task_off[lo]) * ch;
     if (f0 == 0) continue;                               // a clip's first task: rows < kd are 0, written by the fused kernel
     const long long row0 = frame_off[lo];
     const int f = f0 + t;

@@ -375,41 +375,67 @@ int carve_workspace(void *ws, size_t bytes, int n_clips, Workspace &w) {
 }
 
 // Frames per task.  Tasks are pulled from one counter by W workers per GPU (warps of the warp kernels, groups of the
-// others), all of about the same length, so the kernel runs ceil(tasks / W) rounds of (chunk + warm-up rows + a
+// others), all of about the same length, so a launch runs ceil(tasks / W) rounds of (chunk + warm-up rows + a
 // per-task overhead) frames: a chunk that leaves the last round nearly empty wastes up to a whole round (measured on
 // B200, 64 x 18000 frames at frame 1024: 48-frame tasks = 10.15 rounds run 1.409 ms, 16- or 64-frame tasks 1.378 ms,
-// 96-frame tasks = 5.08 rounds 1.486 ms).  The candidate with the smallest modelled cost wins; a small batch
-// (less than one round) gets the smallest tasks so that every SM has work.
-// kd: warm-up rows per task (0 when the seam fix-up forms the first differences, see launch_front).
+// 96-frame tasks = 5.08 rounds 1.486 ms).  Two plans are priced with that model and the cheaper one is taken:
+//   one size   the candidate with the smallest rounds x (chunk + overhead); a small batch (less than one round) gets
+//              the smallest tasks so that every SM has work;
+//   two sizes  long tasks (little overhead) for all clips but the last few, whose short tasks fill the last round:
+//              workers that find no long task left take short ones, and the launch ends within one short task
+//              (needs enough clips that the last ones hold a round of long tasks' worth of frames).
 // per_sm: workers resident per SM (16 warps of the warp kernel, 2-5 groups of the others); overhead: task fetch and
 // the cold L1 of a task's first frames, in frames (0.75 for a warp, 1 for a group: fitted to the measured sweeps).
-int choose_chunk(const b200spec_plan *pl, int per_sm, double overhead, long long total_frames, int n_clips, int kd) {
+// kd: warm-up rows per task (0 when the seam fix-up forms the first differences, see launch_front).
+struct TaskPlan {
+  int chunk, chunk_small, tail_clips;
+};
+
+TaskPlan choose_tasks(const b200spec_plan *pl, int per_sm, double overhead, long long total_frames, int n_clips, int kd) {
   const double workers = (double)pl->num_sms * per_sm;
   const double clips = n_clips > 0 ? (double)n_clips : 1.0;
   const double per_clip = (double)total_frames / clips;
-  static const int cand[] = {2, 4, 8, 12, 16, 20, 24, 28, 32, 40, 48, 56, 64, 72, 80, 96};
-  int best = 16;
-  double best_cost = 1e300;
-  for (int c0 : cand) {
-    int c = c0;
+  auto aligned = [kd](int c) {
     if (c >= 16) c -= (c + kd) % 4;            // a task transforms c + kd frames: whole tail batches (4 frames / pairs)
     else if ((c + kd) & 1) c += 1;             // whole pairs of frames
+    return c;
+  };
+  static const int cand[] = {2, 4, 8, 12, 16, 20, 24, 28, 32, 40, 48, 56, 64, 72, 80, 96};
+  TaskPlan best{16, 16, 0};
+  double best_cost = 1e300;
+  for (int c0 : cand) {
+    const int c = aligned(c0);
     const double tasks = clips * std::ceil(per_clip / c);
     const double rounds = std::max(1.0, std::ceil(tasks / workers));
     const double cost = rounds * (c + kd + overhead);
-    if (cost < best_cost * (1.0 - 1e-9) || (cost <= best_cost * (1.0 + 1e-9) && c > best)) {   // ties: fewer, longer tasks
+    if (cost < best_cost * (1.0 - 1e-9) || (cost <= best_cost * (1.0 + 1e-9) && c > best.chunk)) {   // ties: fewer, longer tasks
       best_cost = cost;
-      best = c;
+      best = TaskPlan{c, c, 0};
     }
   }
-  long long chunk = best;
-#ifdef B200SPEC_TUNING
-  if (const char *e = getenv("B200SPEC_CHUNK")) {   // tuning override
-    const int v = atoi(e);
-    if (v > 0) chunk = v;
+#ifndef B2_ONE_TASK_SIZE   // tuning: -DB2_ONE_TASK_SIZE keeps the one-size plan
+  const int cs = aligned(16);
+  static const int cand_long[] = {48, 64, 80, 96};
+  for (int c0 : cand_long) {
+    const int cb = aligned(c0);
+    const int tail = (int)std::ceil(workers * cb / std::max(per_clip, 1.0));     // clips that hold one round of long tasks
+    if (n_clips < 8 || tail < 1 || tail > n_clips / 2) continue;
+    const double long_tasks = (clips - tail) * std::ceil(per_clip / cb), short_tasks = tail * std::ceil(per_clip / cs);
+    if (long_tasks < 2.0 * workers) continue;                                    // too little work for two phases
+    const double cost = (long_tasks * (cb + kd + overhead) + short_tasks * (cs + kd + overhead)) / workers + (cs + kd + overhead);
+    if (cost < best_cost * (1.0 - 1e-9)) {
+      best_cost = cost;
+      best = TaskPlan{cb, cs, tail};
+    }
   }
 #endif
-  return (int)chunk;
+#ifdef B200SPEC_TUNING
+  if (const char *e = getenv("B200SPEC_CHUNK")) {   // tuning override: one size
+    const int v = atoi(e);
+    if (v > 0) best = TaskPlan{v, v, 0};
+  }
+#endif
+  return best;
 }
 
 // everything of FrontParams that comes from the plan (tables, filterbank, constants)
@@ -512,11 +538,14 @@ int launch_front(const b200spec_plan *pl, int res, int mode, const void *d_sig, 
                          r.d_w32_tw != nullptr && p.proj == nullptr && (r.frame_size == 1024 || r.w32_ns * r.w32_L <= 30);
   const int per_sm = warp_path ? 16 : r.frame_size == 1024 ? 5 : r.frame_size == 2048 ? 4 : 3;
   const double task_overhead = warp_path ? 0.75 : 1.0;   // fitted to the task-size sweeps in profiles/r02_variants.txt
-  const int chunk = choose_chunk(pl, per_sm, task_overhead, total_frames, n_clips,
-                                 (mode == b2::MODE_LOGFILT && !seam_fix) ? r.diff_frames : 0);
+  const TaskPlan tp = choose_tasks(pl, per_sm, task_overhead, total_frames, n_clips,
+                                   (mode == b2::MODE_LOGFILT && !seam_fix) ? r.diff_frames : 0);
+  const int chunk = tp.chunk;
   p.seam_fix = seam_fix ? 1 : 0;
-  b2::k_setup_tasks<<<1, 1024, 0, st>>>(reinterpret_cast<const long long *>(d_frame_off), n_clips, chunk,
-                                         w.task_off, w.counter);
+  p.chunk_small = tp.chunk_small;
+  p.tail_clips = tp.tail_clips;
+  b2::k_setup_tasks<<<1, 1024, 0, st>>>(reinterpret_cast<const long long *>(d_frame_off), n_clips, chunk, tp.chunk_small,
+                                         tp.tail_clips, w.task_off, w.counter);
   CU_CHECK(cudaGetLastError());
   g_launches++;
 
@@ -530,15 +559,15 @@ int launch_front(const b200spec_plan *pl, int res, int mode, const void *d_sig, 
   fill_plan_params(pl, r, p);
 
   const int in = (pl->dtype == B200SPEC_I16 ? 2 : 0) + (pl->channels == 2 ? 1 : 0);
-  const long long task_bound = total_frames / chunk + n_clips;
+  const long long task_bound = total_frames / std::min(chunk, tp.chunk_small) + n_clips;
   cudaError_t e;
   auto seam_fixup = [&]() -> int {
     if (!(seam_fix && want_diff)) return 0;
-    long long warps = task_bound * std::min(r.diff_frames, chunk);
+    long long warps = task_bound * r.diff_frames;
     long long blocks = (warps + 7) / 8;
     if (blocks > pl->num_sms * 8) blocks = pl->num_sms * 8;
     b2::k_seam_diff<<<(int)(blocks < 1 ? 1 : blocks), 256, 0, st>>>(
-        w.task_off, n_clips, chunk, p.frame_off, p.out + p.col_spec, p.ld_out, r.num_bands, r.diff_frames, r.positive,
+        w.task_off, n_clips, chunk, tp.chunk_small, tp.tail_clips, p.frame_off, p.out + p.col_spec, p.ld_out, r.num_bands, r.diff_frames, r.positive,
         p.col_diff >= 0 ? p.out + p.col_diff : nullptr, p.ld_out, p.flux);
     CU_CHECK(cudaGetLastError());
     g_launches++;
@@ -787,7 +816,7 @@ int b200spec_logfilt_multi(const b200spec_plan *plan, int32_t n_res, const int32
   if (chunk < 16) chunk = 16;
   if (chunk > kMultiChunkMax) chunk = kMultiChunkMax;
   if (chunk >= 16) chunk -= (chunk + kd_max) % 4;
-  b2::k_setup_tasks<<<1, 1024, 0, st>>>(reinterpret_cast<const long long *>(d_frame_off), n_clips, (int)chunk,
+  b2::k_setup_tasks<<<1, 1024, 0, st>>>(reinterpret_cast<const long long *>(d_frame_off), n_clips, (int)chunk, (int)chunk, 0,
                                          w.task_off, w.counter);
   CU_CHECK(cudaGetLastError());
   g_launches++;

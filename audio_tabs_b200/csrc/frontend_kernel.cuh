@@ -91,6 +91,9 @@ struct FrontParams {
   // rows of every task (but a clip's first) then hold a difference against a stale ring; k_seam_diff rewrites them
   // from the (log-)filtered rows in global memory once the kernel is done (b200spec.cu: launch_front).
   int seam_fix;
+  // tasks of the LAST tail_clips clips are chunk_small frames long instead of chunk: the counter hands out the long
+  // tasks first, and workers that find no long task left fill the last round with short ones (0 = one size)
+  int chunk_small, tail_clips;
   int spec_complex;
   int circular_shift;   // madmom stft(circular_shift=True) with fft_size == frame_size: the two halves of the windowed
                         // frame are swapped before the transform = bin k times (-1)^k (magnitudes are unchanged)
@@ -101,6 +104,9 @@ struct FrontParams {
   int mag_cap;                                           // floats of a magnitude row that are kept (k_front<8192>: kmax + slack)
   int part_stride;                                       // floats per frame in the partial-sum buffer
 };
+
+// frames per task of clip c (FrontParams::tail_clips)
+B2_HD int task_chunk(const FrontParams &p, int c) { return c >= p.n_clips - p.tail_clips ? p.chunk_small : p.chunk; }
 
 // the projection (chroma fold / PCP) in CSR-by-class form, staged in shared memory: class offsets, bands, weights
 inline size_t proj_table_bytes(const FrontParams &p) {
@@ -502,8 +508,9 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
     const long long nsamp = p.clip_off[c + 1] - samp0;
     const long long row0 = p.frame_off[c];
     const int T = (int)(p.frame_off[c + 1] - row0);
-    const int f0 = (task - p.task_off[c]) * p.chunk;
-    const int f1 = min(T, f0 + p.chunk);
+    const int ch = task_chunk(p, c);
+    const int f0 = (task - p.task_off[c]) * ch;
+    const int f1 = min(T, f0 + ch);
     const int fs = (MODE == MODE_LOGFILT && kd > 0 && !p.seam_fix) ? max(0, f0 - kd) : f0;  // warm-up rows for the diff
     Samples<IN> S{clip_base<IN>(p.sig, samp0)};
     float cscale = (MODE == MODE_LOGFILT && p.clip_scale != nullptr) ? __ldg(p.clip_scale + c) : 1.f;

@@ -353,8 +353,9 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front_pair(const FrontP
     if (task >= total_tasks) break;
     const int c = task_clip(p.task_off, p.n_clips, task);
     const int T = (int)(p.frame_off[c + 1] - p.frame_off[c]);
-    const int f0 = (task - p.task_off[c]) * p.chunk;
-    pair_run_task<P, F, IN, false>(p, smem, gmem, g, tid, tw2r, c, f0, min(T, f0 + p.chunk));
+    const int ch = task_chunk(p, c);
+    const int f0 = (task - p.task_off[c]) * ch;
+    pair_run_task<P, F, IN, false>(p, smem, gmem, g, tid, tw2r, c, f0, min(T, f0 + ch));
   }
 }
 

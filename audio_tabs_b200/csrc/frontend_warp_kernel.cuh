@@ -189,8 +189,9 @@ __global__ void __launch_bounds__(32 * NW, 1) k_front_warp(const FrontParams p) 
     const long long nsamp = p.clip_off[c + 1] - samp0;
     const long long row0 = p.frame_off[c];
     const int Tn = (int)(p.frame_off[c + 1] - row0);
-    const int f0 = (task - p.task_off[c]) * p.chunk;
-    const int f1 = min(Tn, f0 + p.chunk);
+    const int ch = task_chunk(p, c);
+    const int f0 = (task - p.task_off[c]) * ch;
+    const int f1 = min(Tn, f0 + ch);
     const int fs = (kd > 0 && !p.seam_fix) ? max(0, f0 - kd) : f0;     // warm-up rows for the difference
     Samples<IN> S{clip_base<IN>(p.sig, samp0)};
     float cscale = p.clip_scale != nullptr ? __ldg(p.clip_scale + c) : 1.f;

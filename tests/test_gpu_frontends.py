@@ -414,6 +414,31 @@ def test_rows_do_not_depend_on_the_batch(b2):
     assert np.array_equal(batch[5], alone)
 
 
+def test_large_batch_with_two_task_sizes_keeps_rows_bitwise(b2):
+    """A batch large enough for the two-size task plan (long tasks, then short ones from the last clips that fill
+    the last round): clips from the long-task region, from the short-task tail and the very last one must have
+    exactly the rows they get when processed alone; nothing unwritten, nothing non-finite."""
+    import torch
+    from audio_tabs_b200.frontends import beat_specs
+    from audio_tabs_b200.plan import FrontEnd, Packed
+    from audio_tabs_b200.synth import synth_batch_device
+    n_clips, n = 40, 120 * SR
+    dev = torch.device("cuda", 0)
+    sig = synth_batch_device(n_clips, n, seed=77, device=dev)
+    fe = FrontEnd(beat_specs(), device=0)
+    packed = Packed(sig, [n] * n_clips, fe.hop_size)
+    out = torch.full((packed.total_frames, fe.width), float("nan"), dtype=torch.float32, device=dev)
+    fe.run_packed(packed, out)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(out).all())
+    T = packed.total_frames // n_clips
+    for c in (0, 17, 29, 33, n_clips - 1):
+        one = Packed(sig[c * n:(c + 1) * n], [n], fe.hop_size)
+        alone = fe.run_packed(one)
+        torch.cuda.synchronize()
+        assert torch.equal(out[c * T:(c + 1) * T], alone), "clip %d" % c
+
+
 # ---- ingest: per-clip peak + fused peak normalisation (SURVEY §8f N4) ---------------------------
 @pytest.mark.parametrize("dtype,channels", [("f32", 1), ("f32", 2), ("i16", 1), ("i16", 2)])
 def test_clip_peak_and_fused_normalisation(b2, dtype, channels):
