@@ -105,6 +105,18 @@ struct FrontParams {
   int part_stride;                                       // floats per frame in the partial-sum buffer
 };
 
+// samples that only the next step touches are requested ahead of pass 1 (tuning: -DB2_PREFETCH_MODE=1 L2 only, 2 none)
+#ifndef B2_PREFETCH_MODE
+#define B2_PREFETCH_MODE 0
+#endif
+#if B2_PREFETCH_MODE == 0
+#define B2_PREFETCH(ptr) asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr))
+#elif B2_PREFETCH_MODE == 1
+#define B2_PREFETCH(ptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr))
+#else
+#define B2_PREFETCH(ptr) ((void)(ptr))
+#endif
+
 // frames per task of clip c (FrontParams::tail_clips)
 B2_HD int task_chunk(const FrontParams &p, int c) { return c >= p.n_clips - p.tail_clips ? p.chunk_small : p.chunk; }
 
@@ -560,7 +572,7 @@ __global__ void __launch_bounds__(kGroupThreads *G, 1) k_front(const FrontParams
           if (e1 > nsamp * ESZ) e1 = nsamp * ESZ;
           const char *bytes = reinterpret_cast<const char *>(S.base);
           for (long long a = (e0 & ~127LL) + tid * 128; a < e1; a += 32 * 128)
-            if (a >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(bytes + a));
+            if (a >= 0) B2_PREFETCH(bytes + a);
         }
         group_bar(g);
         // ---------------- pass 2: twiddle, DFT16, in place ----------------

@@ -262,7 +262,7 @@ __device__ __forceinline__ void pair_run_task(const FrontParams &p, unsigned cha
         if (e1 > nsamp * ESZ) e1 = nsamp * ESZ;
         const char *bytes = reinterpret_cast<const char *>(S.base);
         for (long long a = (e0 & ~127LL) + tid * 128; a < e1; a += 32 * 128)
-          if (a >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(bytes + a));
+          if (a >= 0) B2_PREFETCH(bytes + a);
       }
       group_bar(g);
       // ---------------- pass 2: twiddle, DFT16, in place ----------------
