@@ -149,52 +149,90 @@ __device__ __forceinline__ float warp_median(float (&v)[NPL], int B, int lane) {
   return (a + b) * 0.5f;
 }
 
-// one warp per output row.  NPL > 0: the row lives in registers (NPL = values per lane, a power of two
-// with 32 * NPL >= B) and the median is a warp bitonic sort; NPL == 0: any B <= 1024, the row goes
-// through dynamic shared memory (B floats per warp) and the median is found by rank counting.
+// One warp per output row; a warp walks a CONTIGUOUS range of rows, so the clip lookup is done once per range and,
+// for lag 1, the lagged row is the one the warp has just had in registers (half the loads).
+// NPL > 0: the row lives in registers (NPL = values per lane, a power of two with 32 * NPL >= B) and the median is a
+// warp bitonic sort -- skipped when more than half of the differences are 0 (they are the smallest values a positive
+// difference can take, so both middle order statistics are 0 then); NPL == 0: any B <= 1024, the row goes through
+// dynamic shared memory (B floats per warp) and the median is found by rank counting.
 template <int NPL>
 __global__ void k_onset_env(const float *__restrict__ L, long long ld_L, int B, const long long *__restrict__ frame_off,
                             int n_clips, long long rows, int lag, float top_db, int aggregate, int shift,
                             const float *__restrict__ clip_max, float *__restrict__ env) {
   extern __shared__ float s_rows[];
+  constexpr int NV = NPL > 0 ? NPL : 1;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   float *row = s_rows + (size_t)wib * B;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long r = warp; r < rows; r += nwarps) {
-    int lo = 0, hi = n_clips;
-    while (hi - lo > 1) {
-      int mid = (lo + hi) >> 1;
-      if (frame_off[mid] <= r) lo = mid; else hi = mid;
-    }
+  const long long per_warp = (rows + nwarps - 1) / nwarps;
+  const long long r0 = warp * per_warp, r1 = min(rows, r0 + per_warp);
+  if (r0 >= r1) return;
+  int lo = 0, hi = n_clips;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (frame_off[mid] <= r0) lo = mid; else hi = mid;
+  }
+  const bool vec4 = NPL == 4 && (ld_L & 3) == 0 && (reinterpret_cast<size_t>(L) & 15) == 0 && lane * 4 + 4 <= B;
+  const int k_hi = B >> 1;
+  float prev[NV];                       // clamped values of the row before (same clip), lag 1 only
+  bool have_prev = false;
+  for (long long r = r0; r < r1; ++r) {
+    while (lo + 1 < n_clips && r >= frame_off[lo + 1]) { ++lo; have_prev = false; }
     const long long t = r - frame_off[lo];          // output index inside the clip
     const long long src = t - shift;                // row whose difference lands here
     if (src < lag) {                                // leading zeros: lag + centre shift (np.pad)
       if (lane == 0) env[r] = 0.f;
+      have_prev = false;
       continue;
     }
     const float floor_db = top_db >= 0.f ? clip_max[lo] - top_db : -INFINITY;
     const float *a = L + (r - shift) * ld_L, *b = a - (long long)lag * ld_L;
     float result;
     if (NPL > 0) {
-      float v[NPL > 0 ? NPL : 1];
-      float sum = 0.f;
+      float cur[NV], v[NV];
+      if (vec4) {
+        const float4 q = *reinterpret_cast<const float4 *>(a + lane * 4);
+        cur[0] = q.x; cur[1 % NV] = q.y; cur[2 % NV] = q.z; cur[3 % NV] = q.w;
+      } else {
 #pragma unroll
-      for (int i = 0; i < (NPL > 0 ? NPL : 1); ++i) {
-        const int j = lane * NPL + i;
+        for (int i = 0; i < NV; ++i) cur[i] = (lane * NPL + i < B) ? a[lane * NPL + i] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) cur[i] = fmaxf(cur[i], floor_db);
+      if (!(lag == 1 && have_prev)) {
+        if (vec4) {
+          const float4 q = *reinterpret_cast<const float4 *>(b + lane * 4);
+          prev[0] = q.x; prev[1 % NV] = q.y; prev[2 % NV] = q.z; prev[3 % NV] = q.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < NV; ++i) prev[i] = (lane * NPL + i < B) ? b[lane * NPL + i] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i) prev[i] = fmaxf(prev[i], floor_db);
+      }
+      float sum = 0.f;
+      int zeros = 0;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
         float d = INFINITY;                         // padding sorts to the top
-        if (j < B) {
-          d = fmaxf(0.f, fmaxf(a[j], floor_db) - fmaxf(b[j], floor_db));
+        if (lane * NPL + i < B) {
+          d = fmaxf(0.f, cur[i] - prev[i]);
           sum += d;
+          zeros += d == 0.f;
         }
         v[i] = d;
+        prev[i] = cur[i];                           // the lagged row of the next one
       }
+      have_prev = true;
       if (aggregate == 0) {
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
         result = sum / (float)B;
+      } else if (__reduce_add_sync(0xffffffffu, zeros) > k_hi) {
+        result = 0.f;                               // ranks 0 .. k_hi are all zeros
       } else {
-        result = warp_median<(NPL > 0 ? NPL : 1)>(v, B, lane);
+        result = warp_median<NV>(v, B, lane);
       }
     } else {
       float sum = 0.f;
@@ -210,7 +248,7 @@ __global__ void k_onset_env(const float *__restrict__ L, long long ld_L, int B, 
       } else {
         __syncwarp();
         // rank of every element (ties broken by index); the two middle order statistics give np.median
-        const int k_hi = B >> 1, k_lo = (B & 1) ? k_hi : k_hi - 1;
+        const int k_lo = (B & 1) ? k_hi : k_hi - 1;
         float v_lo = 0.f, v_hi = 0.f;
         for (int j = lane; j < B; j += 32) {
           const float v = row[j];
