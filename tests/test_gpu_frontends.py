@@ -439,6 +439,45 @@ def test_large_batch_with_two_task_sizes_keeps_rows_bitwise(b2):
         assert torch.equal(out[c * T:(c + 1) * T], alone), "clip %d" % c
 
 
+@pytest.mark.parametrize("bands,context", [(105, 15), (7, 3), (33, 4), (1, 5), (128, 1)])
+def test_context_stack_flat_stream(b2, bands, context):
+    """b200spec_context_stack writes the dense (rows, context*bands) matrix as one flat stream of aligned 128-bit
+    stores: ragged clips (empty and one-row ones included), row widths that are no multiple of four floats, an
+    output pointer that is not 16-byte aligned, a strided input, sentinels before and after -- bit-exact against
+    the per-clip zero-padded stacking (madmom DeepChromaProcessor: FramedSignal(frame_size=15, hop_size=1) + _dcp_flatten)."""
+    import ctypes as C
+    import torch
+    from audio_tabs_b200 import _ffi
+    rng = np.random.default_rng(bands * 100 + context)
+    lens = [37, 0, 1, 260, 5, 0, 1033, 2]
+    T = sum(lens)
+    ld = bands + 3
+    x = rng.standard_normal((T, ld)).astype(np.float32)
+    half, W = context // 2, context * bands
+    want = np.zeros((T, W), np.float32)
+    o = 0
+    for n in lens:
+        for t in range(n):
+            for c in range(context):
+                s_ = t + c - half
+                if 0 <= s_ < n:
+                    want[o + t, c * bands:(c + 1) * bands] = x[o + s_, :bands]
+        o += n
+    dev = torch.device("cuda", 0)
+    xin = torch.from_numpy(x).to(dev)
+    fo = torch.tensor(np.concatenate(([0], np.cumsum(lens))), dtype=torch.int64, device=dev)
+    for shift in (0, 1, 3):                                   # float offset of the output inside its allocation
+        buf = torch.full((T * W + 64,), -7.0, dtype=torch.float32, device=dev)
+        out = buf[16 + shift:16 + shift + T * W]
+        _ffi.check(_ffi.lib().b200spec_context_stack(C.c_void_p(xin.data_ptr()), ld, bands, C.c_void_p(fo.data_ptr()),
+                                                     len(lens), T, context, C.c_void_p(out.data_ptr()),
+                                                     C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        torch.cuda.synchronize()
+        got = out.cpu().numpy().reshape(T, W)
+        assert np.array_equal(got, want), "shift %d" % shift
+        assert bool((buf[:16 + shift] == -7.0).all()) and bool((buf[16 + shift + T * W:] == -7.0).all())
+
+
 # ---- ingest: per-clip peak + fused peak normalisation (SURVEY §8f N4) ---------------------------
 @pytest.mark.parametrize("dtype,channels", [("f32", 1), ("f32", 2), ("i16", 1), ("i16", 2)])
 def test_clip_peak_and_fused_normalisation(b2, dtype, channels):
