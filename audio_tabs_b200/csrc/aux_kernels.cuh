@@ -425,15 +425,19 @@ __global__ void k_diff_flux_proj(const float *__restrict__ L, long long ld_L, co
                                  const float *__restrict__ proj_w, float *__restrict__ out, long long ld_out,
                                  int col_spec, int col_diff, float *__restrict__ flux, float *__restrict__ proj,
                                  long long ld_proj) {
-  const int lane = threadIdx.x & 31;
-  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long r = warp; r < rows; r += nwarps) {
-    int lo = 0, hi = n_clips;
-    while (hi - lo > 1) {
-      int mid = (lo + hi) >> 1;
-      if (frame_off[mid] <= r) lo = mid; else hi = mid;
-    }
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  // a block owns a contiguous range of rows, its warps take them in turn: one clip lookup per warp instead of one
+  // per row, and the lagged row is one a neighbouring warp has just pulled into L1
+  const long long per_block = (rows + gridDim.x - 1) / gridDim.x;
+  const long long r0 = blockIdx.x * per_block + wib, r1 = min(rows, (blockIdx.x + 1) * per_block);
+  if (r0 >= r1) return;
+  int lo = 0, hi = n_clips;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (frame_off[mid] <= r0) lo = mid; else hi = mid;
+  }
+  for (long long r = r0; r < r1; r += wpb) {
+    while (lo + 1 < n_clips && r >= frame_off[lo + 1]) ++lo;
     const long long local = r - frame_off[lo];
     const float *x = L + r * ld_L;
     float fsum = 0.f;
