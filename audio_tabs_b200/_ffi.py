@@ -9,7 +9,7 @@ import ctypes as C
 import os
 from pathlib import Path
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_RES = 4
 MAX_DIFF_FRAMES = 16
 
@@ -110,6 +110,7 @@ SYMBOLS = [
     ("b200spec_plan_num_bands", C.c_int, [C.c_void_p, C.c_int32]),
     ("b200spec_plan_filterbank_layout", C.c_int, [C.c_void_p, C.c_int32, c_int32_p]),
     ("b200spec_launch_count", C.c_int64, []),
+    ("b200spec_task_plan", C.c_int, [C.c_int32, C.c_int32, C.c_double, C.c_int64, C.c_int32, C.c_int32, c_int32_p]),
 ]
 
 _LIB = None

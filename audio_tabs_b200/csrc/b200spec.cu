@@ -391,8 +391,8 @@ struct TaskPlan {
   int chunk, chunk_small, tail_clips;
 };
 
-TaskPlan choose_tasks(const b200spec_plan *pl, int per_sm, double overhead, long long total_frames, int n_clips, int kd) {
-  const double workers = (double)pl->num_sms * per_sm;
+TaskPlan choose_tasks(int num_sms, int per_sm, double overhead, long long total_frames, int n_clips, int kd) {
+  const double workers = (double)num_sms * per_sm;
   const double clips = n_clips > 0 ? (double)n_clips : 1.0;
   const double per_clip = (double)total_frames / clips;
   auto aligned = [kd](int c) {
@@ -538,7 +538,7 @@ int launch_front(const b200spec_plan *pl, int res, int mode, const void *d_sig, 
                          r.d_w32_tw != nullptr && p.proj == nullptr && (r.frame_size == 1024 || r.w32_ns * r.w32_L <= 30);
   const int per_sm = warp_path ? 16 : r.frame_size == 1024 ? 5 : r.frame_size == 2048 ? 4 : 3;
   const double task_overhead = warp_path ? 0.75 : 1.0;   // fitted to the task-size sweeps in profiles/r02_variants.txt
-  const TaskPlan tp = choose_tasks(pl, per_sm, task_overhead, total_frames, n_clips,
+  const TaskPlan tp = choose_tasks(pl->num_sms, per_sm, task_overhead, total_frames, n_clips,
                                    (mode == b2::MODE_LOGFILT && !seam_fix) ? r.diff_frames : 0);
   const int chunk = tp.chunk;
   p.seam_fix = seam_fix ? 1 : 0;
@@ -1018,5 +1018,17 @@ int b200spec_plan_filterbank_layout(const b200spec_plan *plan, int32_t res, int3
 }
 
 int64_t b200spec_launch_count(void) { return g_launches.load(); }
+
+int b200spec_task_plan(int32_t num_sms, int32_t workers_per_sm, double overhead_frames, int64_t total_frames,
+                       int32_t n_clips, int32_t warmup_rows, int32_t out[3]) {
+  if (!out) return fail(B200SPEC_ERR_ARG, "out is NULL");
+  if (num_sms < 1 || workers_per_sm < 1 || total_frames < 0 || n_clips < 0 || warmup_rows < 0 || !(overhead_frames >= 0.0))
+    return fail(B200SPEC_ERR_ARG, "task plan: sizes out of range");
+  const TaskPlan tp = choose_tasks(num_sms, workers_per_sm, overhead_frames, total_frames, n_clips, warmup_rows);
+  out[0] = tp.chunk;
+  out[1] = tp.chunk_small;
+  out[2] = tp.tail_clips;
+  return 0;
+}
 
 }  // extern "C"

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define B200SPEC_ABI_VERSION 6
+#define B200SPEC_ABI_VERSION 7
 #define B200SPEC_MAX_RES 4          /* resolutions per plan (RNNBeatProcessor uses 3) */
 #define B200SPEC_MAX_DIFF_FRAMES 16 /* largest supported diff lag in frames */
 
@@ -270,6 +270,18 @@ int b200spec_plan_num_bands(const b200spec_plan *plan, int32_t res);
 int b200spec_plan_filterbank_layout(const b200spec_plan *plan, int32_t res, int32_t out[6]);
 /* number of kernel launches the library has issued in this process (bench.py's gpu_launches) */
 int64_t b200spec_launch_count(void);
+
+/*
+ * Diagnostic, no GPU needed: the task plan a fused launch would use -- how a batch of n_clips clips with total_frames
+ * frames is cut into tasks for num_sms x workers_per_sm workers (16 warps per SM for the warp kernel, 3-5 groups
+ * for the others) that pull them from one counter.  out[0] = frames per task, out[1] = frames per task of the
+ * last out[2] clips (their short tasks fill the last round; out[2] = 0: one size).  overhead_frames: cost of
+ * starting a task, in frames (0.75 for a warp, 1 for a group); warmup_rows: extra rows a task transforms
+ * (diff_frames for a flux-only call, else 0).  The model: W workers run ceil(tasks / W) rounds of
+ * (frames per task + warmup_rows + overhead_frames); see DESIGN.md section 4, "Tasks".
+ */
+int b200spec_task_plan(int32_t num_sms, int32_t workers_per_sm, double overhead_frames, int64_t total_frames,
+                       int32_t n_clips, int32_t warmup_rows, int32_t out[3]);
 
 #ifdef __cplusplus
 }
